@@ -1,0 +1,109 @@
+/*
+ * <huffman/b200.h> — the C-ABI shim between the host C layer and the sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary for the hot path: plain pointers and sizes, huf_error_t
+ * status, no CUDA or torch types in any signature (a cudaStream_t is passed as void*).
+ * huf_encode()/huf_decode() in the host layer call exactly these entry points; a reference
+ * maintainer replacing the body of the reference's block loops would bind the same symbols
+ * (see INTEGRATION.md for the stub).
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *   huf_b200_encode_*   the per-block body of huf_encode, src/encoder.c:288-374
+ *                       = huf_histogram_populate (src/histogram.c:73-103)
+ *                       + huf_tree_from_histogram (src/tree.c:292-427)
+ *                       + __huf_create_char_coding (src/encoder.c:40-81)
+ *                       + huf_tree_serialize (src/tree.c:233-289)
+ *                       + header emit (src/encoder.c:325-342)
+ *                       + __huf_encode_block (src/encoder.c:85-131)
+ *   huf_b200_decode_*   the per-block body of huf_decode, src/decoder.c:218-276
+ *                       = header parse + bound check (src/decoder.c:220-239)
+ *                       + huf_tree_deserialize (src/tree.c:138-227)
+ *                       + __huf_decode_block (src/decoder.c:34-96)
+ *
+ * All `d_*` pointers are DEVICE pointers, 16-byte aligned (cudaMalloc gives 256).
+ * Functions ending in _async only enqueue work on `stream`; the matching _finish waits for
+ * it and returns the status/size.  One context serves one call at a time.
+ */
+#ifndef HUFFMAN_B200_SHIM_H
+#define HUFFMAN_B200_SHIM_H
+
+#include "../huffman.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct huf_b200_ctx huf_b200_ctx_t;
+
+/* Options for huf_b200_ctx_set_option. */
+enum {
+    /* 0 (default): tree_len > HUF_BTREE_LEN is HUF_ERROR_BTREE_OVERFLOW exactly like the
+     * reference decoder (src/decoder.c:237-239).  1: additionally accept the 1025-element
+     * tree the reference encoder emits for blocks that contain all 256 byte values
+     * (src/encoder.c:270, src/tree.c:264).  Env var HUF_B200_ACCEPT_1025=1 sets the default
+     * for contexts created afterwards (this is how huf_decode() is switched). */
+    HUF_B200_OPT_ACCEPT_1025 = 1,
+};
+
+/* Create a context on CUDA device `device` (< 0: the current device).  Fails with
+ * HUF_ERROR_FATAL when no usable sm_100 device/driver is present: there is no CPU path. */
+huf_error_t huf_b200_ctx_create(huf_b200_ctx_t **ctx, int device);
+huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx);
+huf_error_t huf_b200_ctx_set_option(huf_b200_ctx_t *ctx, int option, int64_t value);
+
+/* Upper bound of the encoded size of `length` bytes at `blocksize` (0 => one block). */
+uint64_t huf_b200_encode_bound(uint64_t length, uint64_t blocksize);
+
+/* Number of blocks huf_encode produces for (length, blocksize). */
+uint64_t huf_b200_block_count(uint64_t length, uint64_t blocksize);
+
+/* Encode d_in[0..length) into d_out (capacity out_capacity bytes, >= encode_bound).
+ * Kernels: K1 segment histogram, K2 per-block code build, block-offset scan, K3 pack. */
+huf_error_t huf_b200_encode_async(huf_b200_ctx_t *ctx, const void *d_in, uint64_t length,
+                                  uint64_t blocksize, void *d_out, uint64_t out_capacity,
+                                  void *stream);
+/* Wait; *out_len = bytes written to d_out. */
+huf_error_t huf_b200_encode_finish(huf_b200_ctx_t *ctx, uint64_t *out_len);
+
+/* After encode_finish: device pointer to u64[nblocks + 1] byte offsets of every block in
+ * d_out (exclusive scan of the compressed block sizes; last entry = total).  This is the
+ * array the host concatenation of per-GPU slabs uses; it never alters the stream bytes. */
+huf_error_t huf_b200_encode_block_offsets(huf_b200_ctx_t *ctx, const uint64_t **d_offsets,
+                                          uint64_t *nblocks);
+
+/* Decode.  d_in holds `avail` readable compressed bytes; blocks are started while the
+ * consumed byte count is < `length` (the reference's loop condition, src/decoder.c:218).
+ * Kernels: K4 header-candidate scan + chain/offset scan, K5 table decode. */
+huf_error_t huf_b200_decode_async(huf_b200_ctx_t *ctx, const void *d_in, uint64_t avail,
+                                  uint64_t length, void *d_out, uint64_t out_capacity,
+                                  void *stream);
+/* Wait; *out_len = decoded bytes valid in d_out, *consumed = compressed bytes consumed.
+ * Returns the reference's error code for the first failing block (earlier blocks' output is
+ * valid), HUF_ERROR_READ_WRITE when a block runs past `avail`. */
+huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *ctx, uint64_t *out_len,
+                                   uint64_t *consumed);
+
+/* Plan only: total decoded size and block count of the stream (runs K4, synchronises).
+ * Used by the host layer to size the output buffer.  `status` receives the error the
+ * decode would stop with (sizes then cover the blocks before it). */
+huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *ctx, const void *d_in, uint64_t avail,
+                                 uint64_t length, uint64_t *out_len, uint64_t *nblocks,
+                                 void *stream);
+
+/* Counters for benches/tests: kernels launched by the last *_async call. */
+uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx);
+
+/* Raw device memory helpers so that non-CUDA hosts (C, ctypes, cgo) can stage buffers
+ * without linking the CUDA runtime themselves. */
+huf_error_t huf_b200_dev_alloc(void **d_ptr, uint64_t bytes);
+huf_error_t huf_b200_dev_free(void *d_ptr);
+huf_error_t huf_b200_copy_h2d(void *d_dst, const void *h_src, uint64_t bytes);
+huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes);
+/* Number of visible CUDA devices (0 when the driver/GPU is missing). */
+int huf_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HUFFMAN_B200_SHIM_H */

@@ -1,0 +1,3 @@
+/* <huffman/encoder.h> — include-path compatibility with the reference's header of this name
+ * [ref: include/huffman/encoder.h].  All declarations live in <huffman.h>. */
+#include "../huffman.h"

@@ -1,0 +1,3 @@
+/* <huffman/symbol.h> — include-path compatibility with the reference's header of this name
+ * [ref: include/huffman/symbol.h].  All declarations live in <huffman.h>. */
+#include "../huffman.h"

@@ -1,0 +1,72 @@
+// common.cuh — shared device helpers for the sm_100a block codec kernels.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hufb200 {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Stream layout constants (reference: src/encoder.c:325-342).
+constexpr int kHdrFixed = 10;        // u64 orig_len + i16 tree_len
+constexpr int kMaxTreeElems = 1025;  // 4 * 256 + 1 (Q1: one more than HUF_BTREE_LEN)
+constexpr int kTreeStride = 1032;    // int16 elements reserved per block in the workspace
+constexpr int kScanThreads = 1024;   // single-CTA scan kernels
+
+// Error codes mirrored from huf_error_t so device code can report them.
+enum : uint32_t {
+    kOk = 0,
+    kErrNoMem = 1,
+    kErrInval = 2,
+    kErrIO = 3,
+    kErrFatal = 4,
+    kErrOverflow = 5,
+    kErrCorrupt = 6,
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_in_cta() { return threadIdx.x >> 5; }
+
+// Streaming 16-byte load: read-only path, do not keep the line in L1.
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_max(uint32_t v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+
+// Inclusive warp prefix sum.
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v)
+{
+    const int l = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(kFull, v, d);
+        if (l >= d) v += o;
+    }
+    return v;
+}
+
+}  // namespace hufb200

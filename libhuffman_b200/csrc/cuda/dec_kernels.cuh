@@ -1,0 +1,786 @@
+// dec_kernels.cuh — sm_100a kernels of the decode path.
+//
+// The stream has no block index (no compressed-length field, reference src/encoder.c:325-342),
+// so block starts are found speculatively and then proven:
+//
+//   K4a k_find<EMIT>   header-candidate scan over every byte offset (signature: tree_len =
+//                      4n+1, tree[0] = 255+n, plausible orig_len), two passes: count per chunk,
+//                      then ordered emit.  Offset `first` is always a candidate (true start).
+//   K4b k_gather/scan  orig_len of each candidate -> exclusive scan -> output offsets.
+//   K5  k_decode       one CTA per candidate block: header parse + tree_len bound check
+//                      (src/decoder.c:220-239), tree -> node arrays + 12-bit lookup table in
+//                      shared memory (replaces huf_tree_deserialize, src/tree.c:138-227),
+//                      self-synchronising speculative sub-block decode with a sync-point
+//                      fix-up loop and a symbol-count scan (replaces __huf_decode_block,
+//                      src/decoder.c:34-96), coalesced output from a shared staging buffer.
+//   K4c k_verify       chain validation: end(j) must equal candidate(j+1); first violation or
+//                      error ends the proven chain.  The host restarts after it if needed, so
+//                      the result is exact; speculation only affects speed.
+#pragma once
+
+#include "common.cuh"
+
+namespace hufb200 {
+
+constexpr int kFindWarps = 8;
+constexpr uint32_t kFindChunk = 4096;  // bytes scanned per warp
+constexpr int kDecThreads = 256;
+constexpr int kLutBits = 12;
+constexpr int kLutSize = 1 << kLutBits;
+constexpr int kMaxNodes = 1026;
+
+// LUT entry (u16): bit15 = LONG (low 11 bits: node reached after kLutBits bits),
+// bit14 = DEAD (low 4 bits: 1-based depth of the bit that walks into an absent child),
+// else  [11:8] code length 1..12, [7:0] symbol.
+constexpr uint16_t kLutLong = 0x8000;
+constexpr uint16_t kLutDead = 0x4000;
+
+struct DecArgs {
+    const uint8_t *in;
+    uint64_t avail;      // readable bytes
+    uint64_t length;     // blocks may start while offset < length
+    uint64_t first;      // proven block start this pass begins at
+    uint64_t out_base;   // output bytes already produced before `first`
+    uint8_t *out;
+    uint64_t out_cap;
+    uint32_t accept_1025;
+    uint32_t count_only; // plan mode: do not write output
+    uint32_t stage_cap;  // bytes of dynamic shared memory usable as output staging
+    // workspace
+    uint32_t *chunk_cnt;   // [nchunks]
+    uint64_t *chunk_off;   // [nchunks + 1]
+    uint64_t *cand;        // [max_cand]  candidate byte offsets, ascending
+    uint64_t *olen;        // [max_cand]  orig_len per candidate
+    uint64_t *out_off;     // [max_cand + 1]
+    uint64_t *end_off;     // [max_cand]  byte offset just past the block
+    uint32_t *blk_status;  // [max_cand]
+    uint64_t max_cand;
+    uint64_t nchunks;
+    uint64_t *result;      // [0] ncand [1] proven blocks [2] status [3] consumed [4] out bytes
+                           // [5] chain complete flag [6] candidates found (may exceed max_cand)
+                           // [7] largest orig_len among the candidates
+};
+
+// ------------------------------------------------------------------------------------------
+// byte-granular, bounds-checked readers
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t rd_u16(const uint8_t *p) { return p[0] | ((uint32_t)p[1] << 8); }
+
+__device__ __forceinline__ uint64_t rd_u64(const uint8_t *p)
+{
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+
+// Full signature test at byte offset `off` (reference encoder output only; foreign streams
+// with other tree shapes are still decoded through the chain restart).
+__device__ __forceinline__ bool header_plausible(const DecArgs &a, uint64_t off)
+{
+    if (off + 12 > a.avail) return false;
+    const uint8_t *p = a.in + off;
+    const uint32_t tl = rd_u16(p + 8);
+    const uint32_t t0 = rd_u16(p + 10);
+    if ((tl & 3u) != 1u || tl < 5u || tl > 1025u) return false;
+    if (t0 != 255u + (tl >> 2)) return false;
+    const uint64_t pay0 = off + kHdrFixed + 2ull * tl;
+    if (pay0 > a.avail) return false;
+    const uint64_t ol = rd_u64(p);
+    if (ol == 0) return false;
+    // every symbol costs at least one bit
+    if (ol > 8ull * (a.avail - pay0)) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4a: candidate scan.  Each warp owns kFindChunk consecutive byte offsets.
+// Pre-filter: byte at offset+11 (high byte of tree[0] = 255+n, n in 1..256) must be 0x01.
+// ------------------------------------------------------------------------------------------
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
+{
+    const int lane = lane_id();
+    const uint64_t chunk = (uint64_t)blockIdx.x * kFindWarps + warp_in_cta();
+    if (chunk >= a.nchunks) return;
+    const uint64_t lim = a.length < a.avail ? a.length : a.avail;  // starts must be < lim
+    const uint64_t c0 = a.first + chunk * kFindChunk;
+    if (EMIT && a.chunk_cnt[chunk] == 0) return;
+
+    uint64_t wr = EMIT ? a.chunk_off[chunk] : 0;
+    uint32_t total = 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+
+    for (uint32_t it = 0; it < kFindChunk / 512; it++) {
+        const uint64_t o0 = c0 + it * 512 + lane * 16;  // this lane tests offsets o0 .. o0+15
+        uint32_t mask = 0;                              // bit i: offset o0+i is a candidate
+        if (o0 < lim) {
+            // bytes o0+11 .. o0+26 decide the pre-filter
+            if (vec_ok && (o0 & 15) == 0 && o0 + 32 <= a.avail) {
+                const uint4 v0 = ld_stream_u4(a.in + o0);
+                const uint4 v1 = ld_stream_u4(a.in + o0 + 16);
+                const uint32_t d[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t pre = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    // bytes at offsets 11+4j .. 14+4j
+                    const uint32_t w = __funnelshift_r(d[2 + j], d[3 + j], 24);
+                    const uint32_t eq = __vcmpeq4(w, 0x01010101u);  // 0xff per matching byte
+                    pre |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u))
+                           << (4 * j);
+                }
+                while (pre) {
+                    const int i = __ffs(pre) - 1;
+                    pre &= pre - 1;
+                    if (o0 + i < lim && header_plausible(a, o0 + i)) mask |= 1u << i;
+                }
+            } else {
+                for (int i = 0; i < 16; i++) {
+                    const uint64_t o = o0 + i;
+                    if (o < lim && o + 12 <= a.avail && a.in[o + 11] == 1 && header_plausible(a, o))
+                        mask |= 1u << i;
+                }
+            }
+            if (o0 == a.first) mask |= 1u;  // the proven start is always block 0
+        }
+        const uint32_t n = __popc(mask);
+        if (!EMIT) {
+            total += n;
+        } else {
+            // ordered emit: lanes in order, offsets in order inside a lane
+            const uint32_t incl = warp_incl_scan(n);
+            uint64_t at = wr + incl - n;
+            uint32_t m = mask;
+            while (m) {
+                const int i = __ffs(m) - 1;
+                m &= m - 1;
+                if (at < a.max_cand) a.cand[at] = o0 + i;
+                at++;
+            }
+            wr += __shfl_sync(kFull, incl, 31);
+        }
+    }
+    if (!EMIT) {
+        total = warp_sum(total);
+        if (lane == 0) a.chunk_cnt[chunk] = total;
+    }
+}
+
+// chunk counts -> exclusive offsets, total candidate count -> result[0].  One CTA.
+__global__ void __launch_bounds__(kScanThreads) k_scan_chunks(DecArgs a)
+{
+    __shared__ uint64_t warp_tot[kScanThreads / 32];
+    const uint64_t n = a.nchunks;
+    const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
+    const uint64_t lo = min(n, per * threadIdx.x);
+    const uint64_t hi = min(n, lo + per);
+    uint64_t sum = 0;
+    for (uint64_t i = lo; i < hi; i++) sum += a.chunk_cnt[i];
+    const uint64_t incl = warp_incl_scan(sum);
+    if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
+    __syncthreads();
+    if (warp_in_cta() == 0) {
+        uint64_t t = warp_tot[lane_id()];
+        uint64_t ti = warp_incl_scan(t);
+        warp_tot[lane_id()] = ti - t;
+    }
+    __syncthreads();
+    uint64_t run = warp_tot[warp_in_cta()] + incl - sum;
+    for (uint64_t i = lo; i < hi; i++) {
+        a.chunk_off[i] = run;
+        run += a.chunk_cnt[i];
+    }
+    if (hi == n && lo < n) {
+        a.chunk_off[n] = run;
+        a.result[0] = run < a.max_cand ? run : a.max_cand;
+        a.result[6] = run;  // > max_cand: workspace too small, the host re-sizes and reruns
+    }
+}
+
+// K4b: orig_len of every candidate (bounded so that the scan cannot overflow).
+__global__ void k_gather(DecArgs a)
+{
+    const uint64_t n = a.result[0];
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t off = a.cand[j];
+        uint64_t ol = 0;
+        if (off + 8 <= a.avail) ol = rd_u64(a.in + off);
+        // a block that cannot complete inside the readable bytes produces no counted output
+        const uint64_t room = a.avail > off ? a.avail - off : 0;
+        if (ol > 8ull * room) ol = 0;
+        a.olen[j] = ol;
+        if (ol) atomicMax(reinterpret_cast<unsigned long long *>(&a.result[7]), (unsigned long long)ol);
+    }
+}
+
+// exclusive scan of olen[0..ncand) -> out_off, with ncand read from device memory.
+__global__ void __launch_bounds__(kScanThreads) k_scan_olen(DecArgs a)
+{
+    __shared__ uint64_t warp_tot[kScanThreads / 32];
+    const uint64_t n = a.result[0];
+    const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
+    const uint64_t lo = min(n, per * threadIdx.x);
+    const uint64_t hi = min(n, lo + per);
+    uint64_t sum = 0;
+    for (uint64_t i = lo; i < hi; i++) sum += a.olen[i];
+    const uint64_t incl = warp_incl_scan(sum);
+    if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
+    __syncthreads();
+    if (warp_in_cta() == 0) {
+        uint64_t t = warp_tot[lane_id()];
+        uint64_t ti = warp_incl_scan(t);
+        warp_tot[lane_id()] = ti - t;
+    }
+    __syncthreads();
+    uint64_t run = a.out_base + warp_tot[warp_in_cta()] + incl - sum;
+    for (uint64_t i = lo; i < hi; i++) {
+        a.out_off[i] = run;
+        run += a.olen[i];
+    }
+    if (hi == n && lo < n) a.out_off[n] = run;
+    if (n == 0 && threadIdx.x == 0) a.out_off[0] = a.out_base;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: block decode.
+// ------------------------------------------------------------------------------------------
+
+struct DecSmem {
+    int16_t elems[kMaxNodes + 6];   // serialised tree as read from the stream
+    int16_t lch[kMaxNodes];         // child node ids, -1 = absent
+    int16_t rch[kMaxNodes];
+    int16_t label[kMaxNodes];
+    uint16_t lut[kLutSize];
+    // terminals of the depth-limited tree, in pre-order == ascending code order
+    uint16_t t_start[kMaxNodes * 2 + 4];  // first LUT index covered
+    uint16_t t_entry[kMaxNodes * 2 + 4];
+    uint8_t t_depth[kMaxNodes * 2 + 4];
+    uint32_t sub_end[kDecThreads + 1];
+    uint32_t warp_tot[kDecThreads / 32];
+    uint32_t n_term;
+    int32_t root;
+    uint32_t hdr_status;
+    uint32_t tree_len;
+    uint64_t orig_len;
+    uint32_t err_pos;     // smallest payload bit position at which the true chain failed
+    uint32_t err_code;
+    uint32_t end_bit;
+    uint32_t changed;
+    uint64_t total_syms;
+};
+
+// MSB-first bit window over the payload, addressed in payload-relative bit positions.
+struct BitReader {
+    const uint8_t *in;
+    uint64_t avail;     // readable bytes of the whole stream
+    uint64_t base_bit;  // global bit position of payload bit 0
+    uint64_t buf;       // next bits, left aligned
+    int have;           // valid bits in buf
+    uint64_t next_word; // index of the next aligned 32-bit word to append
+
+    __device__ __forceinline__ uint32_t word_be(uint64_t wi) const
+    {
+        const uint64_t byte = wi << 2;
+        if (byte + 4 <= avail) return bswap32(reinterpret_cast<const uint32_t *>(in)[wi]);
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (byte + j < avail) v |= (uint32_t)in[byte + j] << (24 - 8 * j);
+        }
+        return v;
+    }
+    __device__ __forceinline__ void seek(uint32_t pos)
+    {
+        const uint64_t g = base_bit + pos;
+        const uint64_t wi = g >> 5;
+        const int sh = (int)(g & 31);
+        buf = (((uint64_t)word_be(wi) << 32) | word_be(wi + 1)) << sh;
+        have = 64 - sh;
+        next_word = wi + 2;
+    }
+    __device__ __forceinline__ uint32_t peek(int bits) const { return (uint32_t)(buf >> (64 - bits)); }
+    __device__ __forceinline__ void skip(int bits)
+    {
+        buf <<= bits;
+        have -= bits;
+        if (have <= 32) {
+            buf |= (uint64_t)word_be(next_word++) << (32 - have);
+            have += 32;
+        }
+    }
+};
+
+// One decode step at payload bit position `pos`.  Returns the symbol (>= 0) and advances, or
+// -1 when the walk dies: then `pos` advances by one bit (any deterministic rule works for a
+// speculative start; for a true start the caller records the error) and *dead_at is the bit
+// position whose consumption walks into the absent child.
+__device__ __forceinline__ int decode_one(const DecSmem &sm, BitReader &br, uint32_t &pos,
+                                          uint32_t *dead_at)
+{
+    const uint16_t e = sm.lut[br.peek(kLutBits)];
+    if (!(e & (kLutLong | kLutDead))) {
+        const int len = e >> 8;
+        br.skip(len);
+        pos += len;
+        return e & 0xff;
+    }
+    if (e & kLutDead) {
+        *dead_at = pos + (e & 0xf) - 1;
+        br.skip(1);
+        pos += 1;
+        return -1;
+    }
+    // long code: continue bit by bit from the node reached after kLutBits bits
+    int node = e & 0x7ff;
+    const uint32_t p0 = pos;
+    br.skip(kLutBits);
+    pos += kLutBits;
+    for (;;) {
+        const int bit = br.peek(1);
+        const int nx = bit ? sm.rch[node] : sm.lch[node];
+        if (nx < 0) {
+            *dead_at = pos;
+            // rewind rule: speculative restart one bit after where this walk began
+            pos = p0 + 1;
+            br.seek(pos);
+            return -1;
+        }
+        br.skip(1);
+        pos += 1;
+        node = nx;
+        if (sm.lch[node] < 0 && sm.rch[node] < 0) return (uint8_t)sm.label[node];
+    }
+}
+
+// Decode from `start` until the position reaches `limit` (a sub-block boundary) or `max_syms`
+// symbols were produced.  Returns the symbol count; *end = position after the last step;
+// *first_dead = earliest dead bit seen (0xffffffff if none) with the symbol index before it.
+template <bool WRITE>
+__device__ __forceinline__ uint32_t decode_span(const DecSmem &sm, BitReader &br, uint32_t start,
+                                                uint32_t limit, uint32_t max_syms, uint8_t *dst,
+                                                uint32_t *end, uint32_t *first_dead,
+                                                uint32_t *syms_before_dead)
+{
+    uint32_t pos = start, n = 0;
+    uint32_t dead = 0xffffffffu, dead_n = 0;
+    br.seek(pos);
+    while (pos < limit && n < max_syms) {
+        uint32_t d = 0;
+        const int s = decode_one(sm, br, pos, &d);
+        if (s >= 0) {
+            if (WRITE) dst[n] = (uint8_t)s;
+            n++;
+        } else if (dead == 0xffffffffu) {
+            dead = d;
+            dead_n = n;
+        }
+    }
+    *end = pos;
+    *first_dead = dead;
+    *syms_before_dead = dead_n;
+    return n;
+}
+
+__global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
+{
+    extern __shared__ __align__(16) uint8_t stage[];
+    __shared__ DecSmem sm;
+    const int tid = threadIdx.x;
+    const uint64_t ncand = a.result[0];
+
+    for (uint64_t j = blockIdx.x; j < ncand; j += gridDim.x) {
+        __syncthreads();
+        const uint64_t off = a.cand[j];
+        const uint64_t next_cand = (j + 1 < ncand) ? a.cand[j + 1] : a.avail;
+
+        // ---- header (src/decoder.c:220-239)
+        if (tid == 0) {
+            uint32_t st = kOk;
+            uint64_t ol = 0;
+            uint32_t tl = 0;
+            if (off + 8 > a.avail) {
+                st = kErrIO;
+            } else {
+                ol = rd_u64(a.in + off);
+                if (off + 10 > a.avail) {
+                    st = kErrIO;
+                } else {
+                    tl = rd_u16(a.in + off + 8);
+                    if (tl >= 0x8000u || tl > (a.accept_1025 ? 1025u : 1024u)) {
+                        st = kErrOverflow;
+                    } else if (off + 10 + 2ull * tl > a.avail) {
+                        st = kErrIO;
+                    }
+                }
+            }
+            sm.hdr_status = st;
+            sm.orig_len = ol;
+            sm.tree_len = tl;
+            sm.err_pos = 0xffffffffu;
+            sm.err_code = kOk;
+            sm.end_bit = 0;
+            sm.n_term = 0;
+            sm.root = -1;
+        }
+        __syncthreads();
+        if (sm.hdr_status != kOk) {
+            if (tid == 0) {
+                a.blk_status[j] = sm.hdr_status;
+                a.end_off[j] = off;
+            }
+            continue;
+        }
+        const uint32_t tl = sm.tree_len;
+        const uint64_t orig_len = sm.orig_len;
+        const uint64_t pay0 = off + kHdrFixed + 2ull * tl;
+        for (uint32_t i = tid; i < tl; i += kDecThreads)
+            sm.elems[i] = (int16_t)rd_u16(a.in + off + kHdrFixed + 2ull * i);
+        for (uint32_t i = tid; i < kLutSize; i += kDecThreads) sm.lut[i] = kLutDead | 1;
+        __syncthreads();
+
+        // ---- tree -> node arrays + terminal list (grammar of src/tree.c:138-208)
+        // One pass with a stack of open child slots: every element fills the top slot; a
+        // node opens two more (left on top).  Elements that run out leave slots absent;
+        // trailing elements are ignored.
+        if (tid == 0) {
+            // slot stack entries: parent node id (or -1 for the root slot) | side << 15,
+            // plus the code prefix (first kLutBits bits) and depth of the slot.
+            // Stored in the staging area's first bytes (not yet in use).
+            uint32_t *stk = reinterpret_cast<uint32_t *>(stage);  // {parent|side, prefix|depth<<16}
+            int sp = 0;
+            uint32_t nodes = 0, nt = 0;
+            stk[0] = 0xffffffffu;
+            stk[1] = 0;  // prefix 0, depth 0
+            sp = 1;
+            uint32_t pos = 0;
+            while (sp > 0) {
+                sp--;
+                const uint32_t who = stk[2 * sp];
+                const uint32_t pd = stk[2 * sp + 1];
+                const uint32_t depth = pd >> 16;
+                const uint32_t prefix = pd & 0xffffu;  // depth (<= kLutBits) leading bits
+                int16_t v = -1;
+                if (pos < tl) v = sm.elems[pos++];
+                int id = -1;
+                if (v != -1) {
+                    id = (int)nodes++;
+                    sm.label[id] = v;
+                    sm.lch[id] = -1;
+                    sm.rch[id] = -1;
+                }
+                if (who == 0xffffffffu) {
+                    sm.root = id;
+                } else if (id >= 0) {
+                    if (who & 0x8000u) sm.rch[who & 0x7fffu] = (int16_t)id;
+                    else sm.lch[who & 0x7fffu] = (int16_t)id;
+                }
+                if (id < 0) {
+                    // absent child: consuming the bit that leads here kills the walk
+                    if (depth >= 1 && depth <= (uint32_t)kLutBits) {
+                        sm.t_start[nt] = (uint16_t)(prefix << (kLutBits - depth));
+                        sm.t_depth[nt] = (uint8_t)depth;
+                        sm.t_entry[nt] = (uint16_t)(kLutDead | depth);
+                        nt++;
+                    }
+                    continue;
+                }
+                // a node with two absent children is a leaf; that is only known after its
+                // two slots were filled, so terminals for real nodes are emitted below by
+                // looking one/two elements ahead.
+                const bool l_absent = !(pos < tl) || sm.elems[pos] == -1;
+                bool leaf = false;
+                if (l_absent) {
+                    const bool r_absent = !(pos + 1 < tl) || sm.elems[pos + 1] == -1;
+                    leaf = r_absent;
+                }
+                if (leaf && depth >= 1) {
+                    // consume its two absent slots right here
+                    if (pos < tl) pos++;
+                    if (pos < tl) pos++;
+                    if (depth <= (uint32_t)kLutBits) {
+                        sm.t_start[nt] = (uint16_t)(prefix << (kLutBits - depth));
+                        sm.t_depth[nt] = (uint8_t)depth;
+                        sm.t_entry[nt] = (uint16_t)((depth << 8) | (uint8_t)v);
+                        nt++;
+                    }
+                    continue;
+                }
+                if (leaf && depth == 0) {
+                    // root without children: every first bit walks into an absent child
+                    if (pos < tl) pos++;
+                    if (pos < tl) pos++;
+                    continue;  // LUT stays all-DEAD(depth 1)
+                }
+                if (depth == (uint32_t)kLutBits) {
+                    // inner node exactly at the table depth: long-code continuation
+                    sm.t_start[nt] = (uint16_t)prefix;
+                    sm.t_depth[nt] = (uint8_t)depth;
+                    sm.t_entry[nt] = (uint16_t)(kLutLong | id);
+                    nt++;
+                }
+                const uint32_t cd = depth + 1;
+                const uint32_t cp = cd <= (uint32_t)kLutBits ? (prefix << 1) : prefix;
+                // right slot below, left slot on top
+                stk[2 * sp] = (uint32_t)id | 0x8000u;
+                stk[2 * sp + 1] = (cd << 16) | (cd <= (uint32_t)kLutBits ? (cp | 1u) : cp);
+                sp++;
+                stk[2 * sp] = (uint32_t)id;
+                stk[2 * sp + 1] = (cd << 16) | cp;
+                sp++;
+            }
+            sm.n_term = nt;
+        }
+        __syncthreads();
+
+        // ---- fill the lookup table from the terminal list (ranges are disjoint)
+        {
+            const uint32_t nt = sm.n_term;
+            for (uint32_t t = tid; t < nt; t += kDecThreads) {
+                const uint32_t span = 1u << (kLutBits - sm.t_depth[t]);
+                if (span <= 64) {
+                    const uint32_t s0 = sm.t_start[t];
+                    const uint16_t e = sm.t_entry[t];
+                    for (uint32_t i = 0; i < span; i++) sm.lut[s0 + i] = e;
+                }
+            }
+            // wide ranges (depth <= 5, at most 63 of them): all threads cooperate
+            for (uint32_t t = 0; t < nt; t++) {
+                const uint32_t d = sm.t_depth[t];
+                if (d >= (uint32_t)kLutBits - 6) continue;
+                const uint32_t span = 1u << (kLutBits - d);
+                const uint32_t s0 = sm.t_start[t];
+                const uint16_t e = sm.t_entry[t];
+                for (uint32_t i = tid; i < span; i += kDecThreads) sm.lut[s0 + i] = e;
+            }
+        }
+        __syncthreads();
+
+        // ---- trivial / impossible blocks
+        if (orig_len == 0) {
+            if (tid == 0) {
+                a.blk_status[j] = kOk;
+                a.end_off[j] = pay0;
+            }
+            continue;
+        }
+        if (sm.root < 0) {  // Q4: absent root with symbols to produce
+            if (tid == 0) {
+                a.blk_status[j] = kErrCorrupt;
+                a.end_off[j] = pay0;
+            }
+            continue;
+        }
+        const uint64_t pay_room_bits = 8ull * (a.avail - pay0);
+        const bool doomed = orig_len > pay_room_bits;  // cannot finish: error is EOF or dead walk
+        if (pay_room_bits >= 0xfffffff0ull || (!doomed && orig_len >= 0xfffffff0ull)) {
+            if (tid == 0) {
+                a.blk_status[j] = kErrFatal;  // block too large for this kernel
+                a.end_off[j] = pay0;
+            }
+            continue;
+        }
+
+        // ---- sub-block split over the guessed payload extent
+        uint64_t guess_bytes = next_cand > pay0 ? next_cand - pay0 : 0;
+        if (guess_bytes > a.avail - pay0) guess_bytes = a.avail - pay0;
+        const uint32_t guess_bits = (uint32_t)(8 * guess_bytes);
+        const uint32_t room_bits = (uint32_t)pay_room_bits;
+        uint32_t sub = (guess_bits + kDecThreads - 1) / kDecThreads;
+        sub = (sub + 31u) & ~31u;
+        if (sub < 64) sub = 64;
+        const uint32_t my_lo = (uint32_t)min((uint64_t)tid * sub, (uint64_t)room_bits);
+        const uint32_t my_hi = (uint32_t)min((uint64_t)(tid + 1) * sub, (uint64_t)room_bits);
+
+        BitReader br;
+        br.in = a.in;
+        br.avail = a.avail;
+        br.base_bit = pay0 << 3;
+        const uint32_t max_syms = doomed ? 0xffffffffu : (uint32_t)orig_len;
+
+        // phase 1: speculative decode of every sub-block from its nominal start
+        uint32_t start = my_lo, end = my_lo, cnt = 0, dead = 0xffffffffu, dead_n = 0;
+        if (my_lo < my_hi)
+            cnt = decode_span<false>(sm, br, start, my_hi, max_syms, nullptr, &end, &dead, &dead_n);
+        sm.sub_end[tid] = end;
+        __syncthreads();
+
+        // phase 2: sync-point fix-up.  Thread t's true start is where thread t-1 ended;
+        // re-decode while that belief changes.  Thread t is final after at most t rounds;
+        // Huffman codes re-synchronise quickly, so in practice after two.
+        for (int round = 0; round < kDecThreads; round++) {
+            const uint32_t want = tid == 0 ? 0u : sm.sub_end[tid - 1];
+            const bool redo = tid > 0 && want != start;
+            __syncthreads();
+            if (redo) {
+                start = want;
+                if (start < my_hi) {
+                    cnt = decode_span<false>(sm, br, start, my_hi, max_syms, nullptr, &end, &dead,
+                                             &dead_n);
+                } else {
+                    cnt = 0;
+                    end = start;
+                    dead = 0xffffffffu;
+                    dead_n = 0;
+                }
+                sm.sub_end[tid] = end;
+            }
+            if (!__syncthreads_or(redo)) break;
+        }
+
+        // phase 3: symbol-count scan -> output index of every sub-block
+        const uint32_t incl = warp_incl_scan(cnt);
+        if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            const uint32_t t = tid < kDecThreads / 32 ? sm.warp_tot[tid] : 0;
+            const uint32_t ti = warp_incl_scan(t);
+            if (tid < kDecThreads / 32) sm.warp_tot[tid] = ti - t;
+        }
+        __syncthreads();
+        const uint64_t before = (uint64_t)sm.warp_tot[tid >> 5] + incl - cnt;  // symbols before mine
+        if (tid == kDecThreads - 1) sm.total_syms = before + cnt;
+
+        // true-chain errors: a dead walk before all needed symbols were produced
+        if (dead != 0xffffffffu && before + dead_n < orig_len) atomicMin(&sm.err_pos, dead);
+
+        uint32_t need = 0;
+        if (before < orig_len) need = (uint32_t)min((uint64_t)cnt, orig_len - before);
+        const bool finisher = need > 0 && before + need == orig_len;
+        const uint64_t out0 = a.out_off[j];
+        const bool can_write = !a.count_only && !doomed && out0 + orig_len <= a.out_cap;
+        const bool use_stage = can_write && orig_len <= a.stage_cap;
+
+        if (need > 0 && (finisher || can_write)) {
+            uint8_t *dst = use_stage ? stage + before : a.out + out0 + before;
+            uint32_t e2, d2, dn2;
+            if (can_write)
+                decode_span<true>(sm, br, start, 0xffffffffu, need, dst, &e2, &d2, &dn2);
+            else
+                decode_span<false>(sm, br, start, 0xffffffffu, need, nullptr, &e2, &d2, &dn2);
+            if (finisher) sm.end_bit = e2;
+        }
+        __syncthreads();
+
+        // The guessed extent was short (the next candidate was a false positive inside this
+        // payload): the chain runs past the last sub-block, whose end is proven by now, and one
+        // thread finishes serially.  Rare by construction of the signature.
+        if (tid == 0 && sm.total_syms < orig_len) {
+            const uint32_t from = sm.sub_end[kDecThreads - 1];
+            const uint64_t have = sm.total_syms;
+            const uint64_t rest = orig_len - have;
+            uint32_t e2 = from, d2 = 0xffffffffu, dn2 = 0, got = 0;
+            if (from < room_bits) {
+                const uint32_t lim_syms = rest > 0xffffffffull ? 0xffffffffu : (uint32_t)rest;
+                uint8_t *dst = use_stage ? stage + have : a.out + out0 + have;
+                if (can_write)
+                    got = decode_span<true>(sm, br, from, room_bits, lim_syms, dst, &e2, &d2, &dn2);
+                else
+                    got = decode_span<false>(sm, br, from, room_bits, lim_syms, nullptr, &e2, &d2, &dn2);
+            }
+            if (d2 != 0xffffffffu) atomicMin(&sm.err_pos, d2);
+            if (got == rest) {
+                sm.end_bit = e2;
+            } else {
+                atomicMin(&sm.err_pos, room_bits);  // ran out of readable bytes
+            }
+        }
+        __syncthreads();
+
+        // A dead walk at a bit the reader could still deliver is BTREE_CORRUPTED; running out
+        // of readable bytes first is READ_WRITE (src/decoder.c:53,69-71).
+        uint32_t status = kOk;
+        if (sm.err_pos != 0xffffffffu) {
+            status = sm.err_pos >= room_bits ? kErrIO : kErrCorrupt;
+        } else if (sm.end_bit > room_bits) {
+            status = kErrIO;  // the finishing code word extends past the readable bytes
+        }
+
+        // ---- output: staged blocks leave through coalesced 16-byte stores
+        if (status == kOk && use_stage) {
+            uint8_t *dst = a.out + out0;
+            const uint32_t n = (uint32_t)orig_len;
+            const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+            for (uint32_t i = tid; i < head; i += kDecThreads) dst[i] = stage[i];
+            const uint32_t body = (n - head) >> 4;
+            if ((head & 3) == 0) {
+                for (uint32_t i = tid; i < body; i += kDecThreads) {
+                    const uint32_t *s = reinterpret_cast<const uint32_t *>(stage + head + 16 * i);
+                    reinterpret_cast<uint4 *>(dst + head)[i] = make_uint4(s[0], s[1], s[2], s[3]);
+                }
+            } else {
+                for (uint32_t i = tid; i < body; i += kDecThreads) {
+                    const uint8_t *s = stage + head + 16 * i;
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        w[q] = s[4 * q] | (s[4 * q + 1] << 8) | (s[4 * q + 2] << 16) |
+                               ((uint32_t)s[4 * q + 3] << 24);
+                    reinterpret_cast<uint4 *>(dst + head)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            for (uint32_t i = head + (body << 4) + tid; i < n; i += kDecThreads) dst[i] = stage[i];
+        }
+        if (tid == 0) {
+            a.blk_status[j] = status;
+            a.end_off[j] = pay0 + (((uint64_t)sm.end_bit + 7) >> 3);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4c: chain validation.  One CTA.
+// result[1] = number of proven blocks, [2] = status of the first failing block (or OK),
+// [3] = byte offset reached, [4] = output bytes produced by the proven blocks,
+// [5] = 1 when the chain reached `length` (or an error) and no restart is needed.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kScanThreads) k_verify(DecArgs a)
+{
+    __shared__ unsigned long long first_bad;
+    const uint64_t n = a.result[0];
+    if (threadIdx.x == 0) first_bad = n;
+    __syncthreads();
+    for (uint64_t j = threadIdx.x; j < n; j += kScanThreads) {
+        bool bad = a.blk_status[j] != kOk;
+        if (!bad && j + 1 < n && a.end_off[j] != a.cand[j + 1]) bad = true;
+        // a block whose output does not fit is not proven either
+        if (!bad && !a.count_only && a.out_off[j] + a.olen[j] > a.out_cap) bad = true;
+        if (bad) atomicMin(&first_bad, (unsigned long long)j);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t fb = first_bad;
+        uint64_t proven = fb, status = kOk, reached, produced, done = 0;
+        if (fb < n && a.blk_status[fb] != kOk) {
+            status = a.blk_status[fb];  // blocks before fb are valid, fb fails: stop here
+            done = 1;
+            reached = fb ? a.end_off[fb - 1] : a.first;
+            produced = a.out_off[fb];
+        } else if (fb < n && !a.count_only && a.out_off[fb] + a.olen[fb] > a.out_cap) {
+            status = kErrNoMem;  // output capacity exhausted (host grows the buffer and resumes)
+            done = 1;
+            reached = fb ? a.end_off[fb - 1] : a.first;
+            produced = a.out_off[fb];
+        } else if (fb < n) {
+            // block fb decoded fine but does not end where the next candidate starts:
+            // fb itself is proven, restart after it
+            proven = fb + 1;
+            reached = a.end_off[fb];
+            produced = a.out_off[fb + 1];
+        } else {
+            reached = n ? a.end_off[n - 1] : a.first;
+            produced = a.out_off[n];
+        }
+        if (!done && reached >= a.length) done = 1;
+        a.result[1] = proven;
+        a.result[2] = status;
+        a.result[3] = reached;
+        a.result[4] = produced;
+        a.result[5] = done;
+    }
+}
+
+}  // namespace hufb200

@@ -1,0 +1,687 @@
+// enc_kernels.cuh — sm_100a kernels of the encode path.
+//
+//   K1  k_seg_hist      one warp per input segment: byte histogram in warp-private shared
+//                       memory counters fed by 16-byte streaming loads; u16[256] per segment.
+//                       Replaces huf_histogram_populate (reference src/histogram.c:73-103).
+//   K2  k_build<W>      one warp per block: block histogram = sum of its segment histograms,
+//                       exact min-pair merge with the reference's tie-break, code words,
+//                       serialised tree, per-segment payload bit offsets, block byte size.
+//                       Replaces huf_tree_from_histogram (src/tree.c:292-427),
+//                       __huf_create_char_coding (src/encoder.c:40-81) + huf_node_to_string
+//                       (src/tree.c:12-47) and huf_tree_serialize (src/tree.c:233-289).
+//       k_scan_sizes    exclusive scan of block byte sizes -> block offsets in the stream.
+//   K3  k_pack          one warp per segment: code lookup, warp scan of code lengths,
+//                       funnel-shift bit packing into a shared staging window, coalesced
+//                       32-bit big-endian word stores; also emits the block header.
+//                       Replaces the header writes (src/encoder.c:325-342) and
+//                       __huf_encode_block + huf_bit_write (src/encoder.c:85-131,
+//                       src/bufio.c:18-32).
+//
+// Data layout in HBM (all sizes for nblocks blocks, nspb segments per block):
+//   seg_hist   u16 [nblocks*nspb][256]    written by K1, read by K2
+//   seg_bitoff u64 [nblocks*nspb]         payload bit offset of each segment inside its block
+//   blk_bits   u64 [nblocks]              payload bits per block
+//   blk_size   u64 [nblocks]              10 + 2*tree_len + ceil(bits/8)
+//   blk_off    u64 [nblocks+1]            exclusive scan of blk_size
+//   blk_table  u32 [nblocks][512]         fmt0: 256 x u32 (code<<(32-len) | len), len <= 26
+//                                         fmt1: 256 x u64 (code<<(64-len) | len), len <= 56
+//   blk_tree   i16 [nblocks][kTreeStride] pre-order tree, -1 = absent child
+//   blk_meta   u32 [nblocks][4]           {tree_len, max_len, fmt, nsym}
+#pragma once
+
+#include "common.cuh"
+
+namespace hufb200 {
+
+struct EncArgs {
+    const uint8_t *in;
+    uint64_t length;
+    uint64_t blocksize;
+    uint64_t nblocks;   // blocks in the whole call
+    uint64_t blk0;      // first block of this pass
+    uint64_t npass;     // blocks in this pass (workspace arrays are indexed pass-locally)
+    uint32_t seg;    // segment size in bytes (multiple of 16, <= 16384)
+    uint32_t nspb;   // segments per full block
+    uint8_t *out;
+    uint64_t out_cap;
+    // workspace
+    uint16_t *seg_hist;
+    uint64_t *seg_bitoff;
+    uint64_t *blk_bits;
+    uint64_t *blk_size;
+    uint64_t *blk_off;
+    uint32_t *blk_table;
+    int16_t *blk_tree;
+    uint32_t *blk_meta;
+    uint32_t *status;  // [0] error code, [1] detail
+};
+
+constexpr int kEncWarps = 8;      // warps per CTA in K1/K3
+constexpr int kBuildWarps = 4;    // warps per CTA in K2
+constexpr uint32_t kNone16 = 0xffffu;
+
+__device__ __forceinline__ uint64_t blk_len_of(const EncArgs &a, uint64_t b)
+{
+    uint64_t start = b * a.blocksize;
+    uint64_t left = a.length - start;
+    return left < a.blocksize ? left : a.blocksize;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: per-segment byte histogram.
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void hist_word(uint32_t *h, uint32_t w)
+{
+    atomicAdd(&h[w & 0xffu], 1u);
+    atomicAdd(&h[(w >> 8) & 0xffu], 1u);
+    atomicAdd(&h[(w >> 16) & 0xffu], 1u);
+    atomicAdd(&h[w >> 24], 1u);
+}
+
+__device__ __forceinline__ void hist_u4(uint32_t *h, const uint4 &v)
+{
+    hist_word(h, v.x);
+    hist_word(h, v.y);
+    hist_word(h, v.z);
+    hist_word(h, v.w);
+}
+
+__global__ void __launch_bounds__(kEncWarps * 32) k_seg_hist(EncArgs a)
+{
+    __shared__ uint32_t sh[kEncWarps][256];
+    const int lane = lane_id();
+    const int w = warp_in_cta();
+    const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
+    if (g >= a.npass * a.nspb) return;
+
+    uint32_t *h = sh[w];
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[lane + 32 * i] = 0;
+    __syncwarp();
+
+    const uint64_t b = a.blk0 + g / a.nspb;
+    const uint32_t k = (uint32_t)(g % a.nspb);
+    const uint64_t blen = blk_len_of(a, b);
+    const uint64_t soff = (uint64_t)k * a.seg;
+    uint32_t slen = 0;
+    if (soff < blen) slen = (uint32_t)((blen - soff) < a.seg ? (blen - soff) : a.seg);
+    const uint8_t *p = a.in + b * a.blocksize + soff;
+
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+        const uint32_t n16 = slen >> 4;
+        uint32_t i = lane;
+        // 4 independent 16-byte loads in flight per lane
+        for (; i + 96 < n16; i += 128) {
+            uint4 v0 = ld_stream_u4(p4 + i);
+            uint4 v1 = ld_stream_u4(p4 + i + 32);
+            uint4 v2 = ld_stream_u4(p4 + i + 64);
+            uint4 v3 = ld_stream_u4(p4 + i + 96);
+            hist_u4(h, v0);
+            hist_u4(h, v1);
+            hist_u4(h, v2);
+            hist_u4(h, v3);
+        }
+        for (; i < n16; i += 32) hist_u4(h, ld_stream_u4(p4 + i));
+        for (uint32_t j = (n16 << 4) + lane; j < slen; j += 32) atomicAdd(&h[p[j]], 1u);
+    } else {
+        for (uint32_t j = lane; j < slen; j += 32) atomicAdd(&h[p[j]], 1u);
+    }
+    __syncwarp();
+
+    // lane l owns bins 8l .. 8l+7 -> one 16-byte store per lane, 512 contiguous bytes per warp
+    uint32_t c[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = h[lane * 8 + i];
+    uint4 o;
+    o.x = c[0] | (c[1] << 16);
+    o.y = c[2] | (c[3] << 16);
+    o.z = c[4] | (c[5] << 16);
+    o.w = c[6] | (c[7] << 16);
+    reinterpret_cast<uint4 *>(a.seg_hist + g * 256)[lane] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: per-block code build.
+// ------------------------------------------------------------------------------------------
+
+template <typename W>
+struct BuildSmem {
+    W key[256];          // block histogram, then leaf keys sorted ascending
+    W iw[256];           // weight of merge node 256 + j
+    uint16_t isz[256];   // serialised size (elements) of the subtree of merge node 256 + j
+    uint16_t lch[256];   // children of merge node 256 + j
+    uint16_t rch[256];
+    uint16_t par[512];   // parent of every node
+    uint8_t len[256];    // code length per symbol (0 = absent)
+};
+
+// Key orders nodes by (weight ascending, node index descending): key = weight << 9 | (511 - idx).
+template <typename W>
+__device__ __forceinline__ W make_key(W weight, uint32_t idx)
+{
+    return (weight << 9) | (W)(511u - idx);
+}
+
+template <typename W>
+__global__ void __launch_bounds__(kBuildWarps * 32) k_build(EncArgs a)
+{
+    __shared__ BuildSmem<W> sm_all[kBuildWarps];
+    const int lane = lane_id();
+    const uint64_t bl = (uint64_t)blockIdx.x * kBuildWarps + warp_in_cta();  // pass-local block
+    if (bl >= a.npass) return;
+    const uint64_t b = a.blk0 + bl;
+    BuildSmem<W> &sm = sm_all[warp_in_cta()];
+    const W kMax = ~(W)0;
+
+    const uint64_t blen = blk_len_of(a, b);
+    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
+    const uint64_t g0 = bl * a.nspb;
+
+    // (1) block histogram: lane owns symbols 8*lane .. 8*lane+7
+    W cnt[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cnt[i] = 0;
+    for (uint32_t k = 0; k < nseg_b; k++) {
+        uint4 v = reinterpret_cast<const uint4 *>(a.seg_hist + (g0 + k) * 256)[lane];
+        cnt[0] += v.x & 0xffffu; cnt[1] += v.x >> 16;
+        cnt[2] += v.y & 0xffffu; cnt[3] += v.y >> 16;
+        cnt[4] += v.z & 0xffffu; cnt[5] += v.z >> 16;
+        cnt[6] += v.w & 0xffffu; cnt[7] += v.w >> 16;
+    }
+    uint32_t present = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t s = lane * 8 + i;
+        sm.key[s] = cnt[i] ? make_key<W>(cnt[i], s) : kMax;
+        present += cnt[i] != 0;
+        sm.len[s] = 0;
+    }
+    const uint32_t n = warp_sum(present);  // distinct symbols, >= 1
+    for (int i = lane; i < 512; i += 32) sm.par[i] = kNone16;
+    __syncwarp();
+
+    // (2) bitonic sort of the 256 leaf keys (absent symbols sort to the end)
+    for (uint32_t k = 2; k <= 256; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (uint32_t t = lane; t < 128; t += 32) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t p = i | j;
+                const bool up = (i & k) == 0;
+                const W x = sm.key[i], y = sm.key[p];
+                if ((x > y) == up) {
+                    sm.key[i] = y;
+                    sm.key[p] = x;
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    // (3) two-queue merge, serial in lane 0.  Leaves are consumed in key order from sm.key;
+    // merge nodes are created with non-decreasing weight, so the live ones are
+    // [head, top) (the front run of equal weight, consumed newest first) plus [nxt, made).
+    if (lane == 0) {
+        uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0;
+        for (;;) {
+            uint32_t pick[2];
+            W pw[2];
+            int got = 0;
+#pragma unroll 1
+            for (int s = 0; s < 2; s++) {
+                if (top == head) {  // front run used up: open the next one
+                    head = nxt;
+                    if (head < made) {
+                        const W rw = sm.iw[head];
+                        uint32_t e = head + 1;
+                        while (e < made && sm.iw[e] == rw) e++;
+                        nxt = top = e;
+                    }
+                } else if (top == nxt) {  // untouched run may have grown at its end
+                    const W rw = sm.iw[head];
+                    while (nxt < made && sm.iw[nxt] == rw) nxt++;
+                    top = nxt;
+                }
+                const bool has_i = top > head;
+                const bool has_l = li < n;
+                if (!has_i && !has_l) break;
+                const W ikey = has_i ? make_key<W>(sm.iw[head], 255u + top) : kMax;
+                const W lkey = has_l ? sm.key[li] : kMax;
+                if (has_i && ikey < lkey) {
+                    top--;
+                    pick[s] = 256u + top;
+                    pw[s] = sm.iw[head];
+                } else {
+                    li++;
+                    pick[s] = 511u - (uint32_t)(lkey & 511u);
+                    pw[s] = lkey >> 9;
+                }
+                got++;
+            }
+            // got >= 1 here: the loop ends right after the unary root is made
+            const uint32_t me = 256u + made;
+            uint32_t size = 1;
+            sm.lch[made] = (uint16_t)pick[0];
+            sm.par[pick[0]] = (uint16_t)me;
+            size += pick[0] < 256u ? 3u : sm.isz[pick[0] - 256u];
+            W weight = pw[0];
+            if (got == 2) {
+                sm.rch[made] = (uint16_t)pick[1];
+                sm.par[pick[1]] = (uint16_t)me;
+                size += pick[1] < 256u ? 3u : sm.isz[pick[1] - 256u];
+                weight += pw[1];
+            } else {
+                sm.rch[made] = (uint16_t)kNone16;
+                size += 1;  // the absent right child of the unary root
+            }
+            sm.iw[made] = weight;
+            sm.isz[made] = (uint16_t)size;
+            made++;
+            if (got < 2) break;
+        }
+    }
+    __syncwarp();
+
+    // (4) climb from every node to the root: code word + pre-order position.
+    const uint32_t root = 255u + n;  // n merge nodes were made
+    const uint32_t tree_len = sm.isz[n - 1];
+    int16_t *tree = a.blk_tree + bl * kTreeStride;
+    uint32_t *tab32 = a.blk_table + bl * 512;
+    uint32_t my_max = 0;
+
+    // leaves first (need code + length), lane handles symbols lane, lane+32, ...
+    uint64_t code_of[8];
+    uint32_t len_of[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t s = lane + 32 * i;
+        uint64_t code = 0;
+        uint32_t len = 0, pos = 0;
+        if (sm.par[s] != kNone16) {
+            uint32_t x = s;
+            while (x != root) {
+                const uint32_t p = sm.par[x];
+                const uint32_t pj = p - 256u;
+                const bool is_right = sm.rch[pj] == x;
+                if (is_right) {
+                    const uint32_t l = sm.lch[pj];
+                    code |= 1ull << len;
+                    pos += l < 256u ? 3u : sm.isz[l - 256u];
+                }
+                pos += 1;
+                len++;
+                x = p;
+            }
+            tree[pos] = (int16_t)s;
+            tree[pos + 1] = -1;
+            tree[pos + 2] = -1;
+            sm.len[s] = (uint8_t)len;
+        }
+        code_of[i] = code;
+        len_of[i] = len;
+        my_max = max(my_max, len);
+    }
+    // merge nodes: position only
+    for (uint32_t v = 256u + lane; v <= root; v += 32) {
+        uint32_t pos = 0, x = v;
+        while (x != root) {
+            const uint32_t p = sm.par[x];
+            const uint32_t pj = p - 256u;
+            if (sm.rch[pj] == x) {
+                const uint32_t l = sm.lch[pj];
+                pos += l < 256u ? 3u : sm.isz[l - 256u];
+            }
+            pos += 1;
+            x = p;
+        }
+        tree[pos] = (int16_t)v;
+    }
+    if (lane == 0) tree[tree_len - 1] = -1;  // absent right child of the unary root
+
+    const uint32_t max_len = warp_max(my_max);
+    const uint32_t fmt = max_len <= 26 ? 0u : 1u;
+    if (max_len > 56 && lane == 0) {
+        atomicMax(&a.status[0], (uint32_t)kErrFatal);
+        a.status[1] = max_len;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t s = lane + 32 * i;
+        const uint32_t len = len_of[i];
+        if (fmt == 0) {
+            tab32[s] = len ? ((uint32_t)code_of[i] << (32 - len)) | len : 0u;
+        } else {
+            const uint64_t e = len ? (code_of[i] << (64 - len)) | len : 0ull;
+            reinterpret_cast<uint64_t *>(tab32)[s] = e;
+        }
+    }
+    __syncwarp();
+
+    // (5) payload bit offset of every segment = running dot(segment histogram, code length)
+    uint32_t l8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) l8[i] = sm.len[lane * 8 + i];
+    uint64_t run = 0;
+    for (uint32_t k = 0; k < nseg_b; k++) {
+        uint4 v = reinterpret_cast<const uint4 *>(a.seg_hist + (g0 + k) * 256)[lane];
+        uint32_t d = (v.x & 0xffffu) * l8[0] + (v.x >> 16) * l8[1] +
+                     (v.y & 0xffffu) * l8[2] + (v.y >> 16) * l8[3] +
+                     (v.z & 0xffffu) * l8[4] + (v.z >> 16) * l8[5] +
+                     (v.w & 0xffffu) * l8[6] + (v.w >> 16) * l8[7];
+        d = warp_sum(d);
+        if (lane == 0) a.seg_bitoff[g0 + k] = run;
+        run += d;
+    }
+    if (lane == 0) {
+        a.blk_bits[bl] = run;
+        a.blk_size[b] = (uint64_t)kHdrFixed + 2ull * tree_len + ((run + 7) >> 3);
+        uint32_t *m = a.blk_meta + bl * 4;
+        m[0] = tree_len;
+        m[1] = max_len;
+        m[2] = fmt;
+        m[3] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block-offset scan: blk_off[i] = sum_{j<i} blk_size[j], blk_off[n] = total.  One CTA.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_sizes(const uint64_t *__restrict__ in,
+                                                             uint64_t *__restrict__ out,
+                                                             uint64_t n, uint64_t cap,
+                                                             uint32_t *status)
+{
+    __shared__ uint64_t warp_tot[kScanThreads / 32];
+    const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
+    const uint64_t lo = min(n, per * threadIdx.x);
+    const uint64_t hi = min(n, lo + per);
+
+    uint64_t sum = 0;
+    for (uint64_t i = lo; i < hi; i++) sum += in[i];
+
+    const uint64_t incl = warp_incl_scan(sum);
+    if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
+    __syncthreads();
+    if (warp_in_cta() == 0) {
+        uint64_t t = warp_tot[lane_id()];
+        uint64_t ti = warp_incl_scan(t);
+        warp_tot[lane_id()] = ti - t;  // exclusive
+    }
+    __syncthreads();
+    // out[0] holds the running total of the previous passes (0 for the first pass)
+    const uint64_t base = out[0];
+    __syncthreads();
+    uint64_t run = base + warp_tot[warp_in_cta()] + incl - sum;
+    for (uint64_t i = lo; i < hi; i++) {
+        out[i] = run;
+        run += in[i];
+    }
+    if (hi == n && lo < n) {
+        out[n] = run;
+        if (run > cap) atomicMax(&status[0], (uint32_t)kErrNoMem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: bit packing.
+// ------------------------------------------------------------------------------------------
+
+constexpr int kStageWords = 424;  // 512 symbols * 26 bits / 32 + slack
+
+struct PackSmem {
+    uint32_t table[kEncWarps][512];       // per-warp copy of the block's code table
+    uint32_t stage[kEncWarps][kStageWords];
+};
+
+// Owned output byte range of one warp and the store helpers that respect it.
+struct OutRange {
+    uint8_t *out;
+    uint64_t b0, b1;          // owned bytes [b0, b1)
+    uint64_t full_lo, full_hi;  // word indices fully inside the owned range
+};
+
+__device__ __forceinline__ void store_word(const OutRange &r, uint64_t widx, uint32_t be)
+{
+    if (widx >= r.full_lo && widx < r.full_hi) {
+        reinterpret_cast<uint32_t *>(r.out)[widx] = bswap32(be);
+    } else {
+        const uint64_t base = widx << 2;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t addr = base + j;
+            if (addr >= r.b0 && addr < r.b1) r.out[addr] = (uint8_t)(be >> (24 - 8 * j));
+        }
+    }
+}
+
+// Insert the top `l` bits of `t` (left aligned, other bits zero) at bit `nb` of the hi:lo
+// window; flush a finished 32-bit word into the staging buffer.
+struct BitAcc {
+    uint32_t hi, lo, nb, widx;
+    bool first;
+};
+
+__device__ __forceinline__ void acc_put(BitAcc &s, uint32_t *stage, uint32_t t, uint32_t l)
+{
+    s.hi |= t >> s.nb;
+    s.lo |= __funnelshift_r(0u, t, s.nb);
+    s.nb += l;
+    if (s.nb >= 32) {
+        if (s.first) {
+            atomicOr(&stage[s.widx], s.hi);  // word shared with the previous lane
+            s.first = false;
+        } else {
+            stage[s.widx] = s.hi;
+        }
+        s.hi = s.lo;
+        s.lo = 0;
+        s.nb -= 32;
+        s.widx++;
+    }
+}
+
+__global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
+{
+    __shared__ PackSmem sm;
+    const int lane = lane_id();
+    const int w = warp_in_cta();
+    const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
+    if (g >= a.npass * a.nspb) return;
+    if (a.status[0] != kOk) return;
+
+    const uint64_t bl = g / a.nspb;
+    const uint64_t b = a.blk0 + bl;
+    const uint32_t k = (uint32_t)(g % a.nspb);
+    const uint64_t blen = blk_len_of(a, b);
+    const uint64_t soff = (uint64_t)k * a.seg;
+    if (soff >= blen) return;
+    const uint32_t slen = (uint32_t)((blen - soff) < a.seg ? (blen - soff) : a.seg);
+    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
+    const uint8_t *blk_in = a.in + b * a.blocksize;
+    const uint8_t *p = blk_in + soff;
+
+    const uint32_t *meta = a.blk_meta + bl * 4;
+    const uint32_t tree_len = meta[0];
+    const uint32_t fmt = meta[2];
+    const uint64_t boff = a.blk_off[b];
+    const uint64_t pay0 = boff + kHdrFixed + 2ull * tree_len;  // first payload byte
+    const uint64_t bits_total = a.blk_bits[bl];
+    const uint64_t o = a.seg_bitoff[g];
+    const bool last_seg = (k + 1 == nseg_b);
+    const uint64_t o_end = last_seg ? bits_total : a.seg_bitoff[g + 1];
+
+    // block header: written by the warp that owns segment 0
+    if (k == 0) {
+        const int16_t *tree = a.blk_tree + bl * kTreeStride;
+        const uint32_t hlen = kHdrFixed + 2 * tree_len;
+        uint8_t *dst = a.out + boff;
+        for (uint32_t i = lane; i < hlen; i += 32) {
+            uint32_t v;
+            if (i < 8) {
+                v = (uint32_t)(blen >> (8 * i));
+            } else if (i < 10) {
+                v = tree_len >> (8 * (i - 8));
+            } else {
+                v = (uint32_t)(uint16_t)tree[(i - 10) >> 1] >> (8 * (i & 1));
+            }
+            dst[i] = (uint8_t)v;
+        }
+    }
+
+    // per-warp copy of the code table
+    uint32_t *tab = sm.table[w];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.blk_table + bl * 512);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        const int n16 = fmt == 0 ? 64 : 128;
+        for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+
+    OutRange r;
+    r.out = a.out;
+    r.b0 = pay0 + (o >> 3);
+    r.b1 = last_seg ? pay0 + ((bits_total + 7) >> 3) : pay0 + (o_end >> 3);
+    r.full_lo = (r.b0 + 3) >> 2;
+    r.full_hi = r.b1 >> 2;
+
+    // Global bit cursor.  The first byte of the segment may begin with the last bits of the
+    // previous segment's final code words: rebuild them so this warp owns the whole byte.
+    uint64_t gbit = (pay0 << 3) + o;
+    uint32_t q = (uint32_t)(gbit & 31);
+    uint64_t wbase = gbit >> 5;
+    uint32_t carry = 0;
+    {
+        const uint32_t rb = (uint32_t)(o & 7);
+        if (rb) {
+            uint32_t val = 0;
+            if (lane == 0) {
+                uint32_t got = 0;
+                uint64_t idx = soff;
+                while (got < rb) {
+                    idx--;
+                    const uint32_t s = blk_in[idx];
+                    uint32_t c, l;
+                    if (fmt == 0) {
+                        const uint32_t e = tab[s];
+                        l = e & 31u;
+                        c = (e & ~31u) >> (32 - l);
+                    } else {
+                        const uint64_t e = reinterpret_cast<const uint64_t *>(tab)[s];
+                        l = (uint32_t)(e & 0xffu);
+                        c = (uint32_t)((e & ~0xffull) >> (64 - l));  // low bits suffice
+                    }
+                    val |= c << got;
+                    got += l;
+                }
+                val &= (1u << rb) - 1u;
+            }
+            val = __shfl_sync(kFull, val, 0);
+            carry = val << (32 - q);
+        }
+    }
+
+    uint32_t *stage = sm.stage[w];
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    const int per_lane = fmt == 0 ? 16 : 4;              // symbols per lane per iteration
+    const uint32_t step = 32u * per_lane;
+
+    for (uint32_t base = 0; base < slen; base += step) {
+        // ---- load this lane's symbols
+        const uint32_t my0 = base + lane * per_lane;
+        uint32_t sym[4] = {0, 0, 0, 0};  // 16 bytes, little endian in words
+        uint32_t nvalid = 0;
+        if (my0 < slen) nvalid = min((uint32_t)per_lane, slen - my0);
+        if (per_lane == 16 && aligned && nvalid == 16) {
+            const uint4 v = ld_stream_u4(p + my0);
+            sym[0] = v.x; sym[1] = v.y; sym[2] = v.z; sym[3] = v.w;
+        } else {
+            // ragged tail / unaligned input: byte loads, static register indices
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((uint32_t)j < nvalid) sym[j >> 2] |= (uint32_t)p[my0 + j] << (8 * (j & 3));
+            }
+        }
+
+        uint32_t total_l = 0;
+        BitAcc acc;
+        if (fmt == 0) {
+            // ---- look up code words, sum the lengths
+            uint32_t e[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t s = (sym[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                e[j] = (uint32_t)j < nvalid ? tab[s] : 0u;
+                total_l += e[j] & 31u;
+            }
+            const uint32_t incl = warp_incl_scan(total_l);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            const uint32_t start = q + incl - total_l;
+            const uint32_t nwords = (q + total + 31) >> 5;
+
+            // ---- staging window: word 0 carries the unfinished word of the previous step
+            for (uint32_t i = lane; i < nwords + 1; i += 32) stage[i] = i ? 0u : carry;
+            __syncwarp();
+
+            acc.hi = acc.lo = 0;
+            acc.nb = start & 31;
+            acc.widx = start >> 5;
+            acc.first = true;
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc_put(acc, stage, e[j] & ~31u, e[j] & 31u);
+            if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
+            __syncwarp();
+
+            // ---- copy finished words out, coalesced
+            const uint32_t nfull = (q + total) >> 5;
+            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
+            q = (q + total) & 31;
+            carry = q ? stage[nfull] : 0u;
+            wbase += nfull;
+            __syncwarp();
+        } else {
+            uint64_t e[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t s = (sym[0] >> (8 * j)) & 0xffu;
+                e[j] = (uint32_t)j < nvalid ? reinterpret_cast<const uint64_t *>(tab)[s] : 0ull;
+                total_l += (uint32_t)(e[j] & 0xffu);
+            }
+            const uint32_t incl = warp_incl_scan(total_l);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            const uint32_t start = q + incl - total_l;
+            const uint32_t nwords = (q + total + 31) >> 5;
+            for (uint32_t i = lane; i < nwords + 1; i += 32) stage[i] = i ? 0u : carry;
+            __syncwarp();
+
+            acc.hi = acc.lo = 0;
+            acc.nb = start & 31;
+            acc.widx = start >> 5;
+            acc.first = true;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t l = (uint32_t)(e[j] & 0xffu);
+                const uint64_t t = e[j] & ~0xffull;
+                const uint32_t l1 = min(l, 32u);
+                acc_put(acc, stage, (uint32_t)(t >> 32), l1);
+                acc_put(acc, stage, (uint32_t)t, l - l1);
+            }
+            if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
+            __syncwarp();
+
+            const uint32_t nfull = (q + total) >> 5;
+            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
+            q = (q + total) & 31;
+            carry = q ? stage[nfull] : 0u;
+            wbase += nfull;
+            __syncwarp();
+        }
+    }
+    // trailing partial word: only its owned bytes are written
+    if (q && lane == 0) store_word(r, wbase, carry);
+}
+
+}  // namespace hufb200

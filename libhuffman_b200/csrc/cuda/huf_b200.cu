@@ -1,0 +1,526 @@
+// huf_b200.cu — the C-ABI shim declared in <huffman/b200.h>: context, device workspace,
+// kernel launches.  Host code above this file is plain C; nothing below it runs on the CPU
+// except launch orchestration.  Compiled for sm_100a only.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include <huffman/b200.h>
+
+#include "dec_kernels.cuh"
+#include "enc_kernels.cuh"
+
+using namespace hufb200;
+
+namespace {
+
+constexpr uint32_t kSegMax = 16384;            // bytes per segment (u16 counters suffice)
+constexpr uint64_t kMaxPassBlocks = 1u << 18;  // blocks per encode pass (bounds the workspace)
+constexpr uint64_t kW32MaxBlock = 4u << 20;    // blocks up to 4 MiB use 32-bit merge keys
+
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t cap = 0;
+    size_t used = 0;
+
+    bool reserve(size_t bytes)
+    {
+        used = 0;
+        if (bytes <= cap) return true;
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+        // grow with headroom so that repeated calls of similar size do not reallocate
+        size_t want = bytes + bytes / 8 + (1u << 20);
+        if (cudaMalloc(&base, want) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        cap = want;
+        return true;
+    }
+    template <typename T>
+    T *take(size_t count)
+    {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
+    }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+}  // namespace
+
+struct huf_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t cur = nullptr;
+    Arena enc_ws, dec_ws;
+    uint32_t *d_status = nullptr;   // [4]
+    uint64_t *d_result = nullptr;   // [8]
+    uint64_t *h_result = nullptr;   // pinned mirror, [16]
+    uint64_t launches = 0;
+    int accept_1025 = 0;
+
+    // encode call in flight
+    bool enc_pending = false;
+    EncArgs enc{};
+    uint64_t *d_blk_off = nullptr;  // [nblocks + 1], lives in enc_ws
+    uint64_t enc_nblocks = 0;
+
+    // decode call in flight
+    bool dec_pending = false;
+    DecArgs dec{};
+    uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode
+    uint64_t dec_stage_want = 65536;
+};
+
+namespace {
+
+huf_error_t cuda_fail(cudaError_t e)
+{
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? HUF_ERROR_MEMORY_ALLOCATION : HUF_ERROR_FATAL;
+}
+
+#define CU_TRY(expr)                                   \
+    do {                                               \
+        cudaError_t e__ = (expr);                      \
+        if (e__ != cudaSuccess) return cuda_fail(e__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+uint32_t pick_seg(uint64_t blocksize)
+{
+    uint64_t s = blocksize < kSegMax ? blocksize : kSegMax;
+    s = (s + 15) & ~uint64_t(15);
+    return (uint32_t)(s ? s : 16);
+}
+
+}  // namespace
+
+extern "C" {
+
+int huf_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+huf_error_t huf_b200_ctx_create(huf_b200_ctx_t **out, int device)
+{
+    if (!out) return HUF_ERROR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (huf_b200_device_count() <= 0) return HUF_ERROR_FATAL;  // no GPU: no CPU path either
+    if (device < 0) CU_TRY(cudaGetDevice(&device));
+
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return HUF_ERROR_FATAL;  // kernels are built for sm_100a only
+
+    DeviceGuard g(device);
+    if (!g.ok) return HUF_ERROR_FATAL;
+    huf_b200_ctx *c = new (std::nothrow) huf_b200_ctx();
+    if (!c) return HUF_ERROR_MEMORY_ALLOCATION;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    const char *env = getenv("HUF_B200_ACCEPT_1025");
+    c->accept_1025 = env && env[0] == '1';
+    cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_status, 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_result, 8 * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_result, 16 * sizeof(uint64_t));
+    if (e != cudaSuccess) {
+        huf_b200_ctx_destroy(&c);
+        return cuda_fail(e);
+    }
+    *out = c;
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx)
+{
+    if (!ctx) return HUF_ERROR_INVALID_ARGUMENT;
+    huf_b200_ctx *c = *ctx;
+    if (c) {
+        DeviceGuard g(c->device);
+        cudaDeviceSynchronize();
+        if (c->enc_ws.base) cudaFree(c->enc_ws.base);
+        if (c->dec_ws.base) cudaFree(c->dec_ws.base);
+        if (c->d_status) cudaFree(c->d_status);
+        if (c->d_result) cudaFree(c->d_result);
+        if (c->h_result) cudaFreeHost(c->h_result);
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        delete c;
+    }
+    *ctx = nullptr;
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_ctx_set_option(huf_b200_ctx_t *ctx, int option, int64_t value)
+{
+    if (!ctx) return HUF_ERROR_INVALID_ARGUMENT;
+    switch (option) {
+    case HUF_B200_OPT_ACCEPT_1025:
+        ctx->accept_1025 = value != 0;
+        return HUF_ERROR_SUCCESS;
+    default:
+        return HUF_ERROR_INVALID_ARGUMENT;
+    }
+}
+
+uint64_t huf_b200_block_count(uint64_t length, uint64_t blocksize)
+{
+    if (!length) return 0;
+    if (!blocksize) blocksize = length;
+    return (length + blocksize - 1) / blocksize;
+}
+
+uint64_t huf_b200_encode_bound(uint64_t length, uint64_t blocksize)
+{
+    // per block: 10 + 2*1025 header bytes; payload < 10 bits per symbol is the true bound for a
+    // 256-symbol alphabet with the extra root bit, rounded up per block
+    const uint64_t nb = huf_b200_block_count(length, blocksize);
+    return nb * (kHdrFixed + 2 * kMaxTreeElems + 8) + length + length / 4 + 16;
+}
+
+uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------
+
+huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t length,
+                                  uint64_t blocksize, void *d_out, uint64_t out_capacity,
+                                  void *stream)
+{
+    if (!c || (!d_in && length) || (!d_out && length)) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    DeviceGuard g(c->device);
+    if (!g.ok) return HUF_ERROR_FATAL;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->own_stream;
+    c->cur = st;
+    c->launches = 0;
+    if (!blocksize) blocksize = length;
+
+    const uint64_t nblocks = huf_b200_block_count(length, blocksize);
+    c->enc_nblocks = nblocks;
+    c->enc_pending = true;
+    EncArgs &a = c->enc;
+    memset(&a, 0, sizeof(a));
+    if (!nblocks) return HUF_ERROR_SUCCESS;
+
+    a.in = static_cast<const uint8_t *>(d_in);
+    a.length = length;
+    a.blocksize = blocksize;
+    a.nblocks = nblocks;
+    a.seg = pick_seg(blocksize);
+    const uint64_t nspb64 = (blocksize + a.seg - 1) / a.seg;
+    if (nspb64 > 0xffffffffull) return HUF_ERROR_INVALID_ARGUMENT;
+    a.nspb = (uint32_t)nspb64;
+    a.out = static_cast<uint8_t *>(d_out);
+    a.out_cap = out_capacity;
+
+    // pass size: bounded by block count and by ~1 GiB of segment histograms
+    uint64_t per_pass = nblocks < kMaxPassBlocks ? nblocks : kMaxPassBlocks;
+    const uint64_t seg_cap = (1ull << 21);  // segments per pass
+    if (per_pass * a.nspb > seg_cap) per_pass = seg_cap / a.nspb ? seg_cap / a.nspb : 1;
+    const uint64_t nseg_pass = per_pass * a.nspb;
+
+    size_t need = 0;
+    need += Arena::padded(nseg_pass * 256 * sizeof(uint16_t));
+    need += Arena::padded(nseg_pass * sizeof(uint64_t));
+    need += Arena::padded(per_pass * sizeof(uint64_t));          // blk_bits
+    need += Arena::padded(nblocks * sizeof(uint64_t));           // blk_size
+    need += Arena::padded((nblocks + 1) * sizeof(uint64_t));     // blk_off
+    need += Arena::padded(per_pass * 512 * sizeof(uint32_t));    // blk_table
+    need += Arena::padded(per_pass * kTreeStride * sizeof(int16_t));
+    need += Arena::padded(per_pass * 4 * sizeof(uint32_t));
+    if (!c->enc_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
+    a.seg_hist = c->enc_ws.take<uint16_t>(nseg_pass * 256);
+    a.seg_bitoff = c->enc_ws.take<uint64_t>(nseg_pass);
+    a.blk_bits = c->enc_ws.take<uint64_t>(per_pass);
+    a.blk_size = c->enc_ws.take<uint64_t>(nblocks);
+    a.blk_off = c->enc_ws.take<uint64_t>(nblocks + 1);
+    a.blk_table = c->enc_ws.take<uint32_t>(per_pass * 512);
+    a.blk_tree = c->enc_ws.take<int16_t>(per_pass * kTreeStride);
+    a.blk_meta = c->enc_ws.take<uint32_t>(per_pass * 4);
+    a.status = c->d_status;
+    c->d_blk_off = a.blk_off;
+
+    CU_TRY(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(a.blk_off, 0, sizeof(uint64_t), st));
+
+    for (uint64_t blk0 = 0; blk0 < nblocks; blk0 += per_pass) {
+        a.blk0 = blk0;
+        a.npass = nblocks - blk0 < per_pass ? nblocks - blk0 : per_pass;
+        const uint64_t nseg = a.npass * a.nspb;
+        const unsigned seg_grid = (unsigned)((nseg + kEncWarps - 1) / kEncWarps);
+        const unsigned bld_grid = (unsigned)((a.npass + kBuildWarps - 1) / kBuildWarps);
+
+        k_seg_hist<<<seg_grid, kEncWarps * 32, 0, st>>>(a);
+        if (blocksize <= kW32MaxBlock)
+            k_build<uint32_t><<<bld_grid, kBuildWarps * 32, 0, st>>>(a);
+        else
+            k_build<uint64_t><<<bld_grid, kBuildWarps * 32, 0, st>>>(a);
+        k_scan_sizes<<<1, kScanThreads, 0, st>>>(a.blk_size + blk0, a.blk_off + blk0, a.npass,
+                                                 a.out_cap, a.status);
+        k_pack<<<seg_grid, kEncWarps * 32, 0, st>>>(a);
+        c->launches += 4;
+    }
+    CU_TRY(cudaGetLastError());
+    // result: total size + status, copied to the pinned mirror on the same stream
+    CU_TRY(cudaMemcpyAsync(&c->h_result[0], a.blk_off + nblocks, sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&c->h_result[1], c->d_status, 2 * sizeof(uint32_t),
+                           cudaMemcpyDeviceToHost, st));
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_encode_finish(huf_b200_ctx_t *c, uint64_t *out_len)
+{
+    if (!c || !out_len) return HUF_ERROR_INVALID_ARGUMENT;
+    if (!c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    c->enc_pending = false;
+    *out_len = 0;
+    if (!c->enc_nblocks) return HUF_ERROR_SUCCESS;
+    DeviceGuard g(c->device);
+    CU_TRY(cudaStreamSynchronize(c->cur));
+    const uint32_t status = (uint32_t)(c->h_result[1] & 0xffffffffu);
+    if (status != kOk) return (huf_error_t)status;
+    *out_len = c->h_result[0];
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_encode_block_offsets(huf_b200_ctx_t *c, const uint64_t **d_offsets,
+                                          uint64_t *nblocks)
+{
+    if (!c || !d_offsets || !nblocks) return HUF_ERROR_INVALID_ARGUMENT;
+    *d_offsets = c->d_blk_off;
+    *nblocks = c->enc_nblocks;
+    return HUF_ERROR_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------
+
+namespace {
+
+// Enqueue one speculative pass starting at the proven block start `first`.
+huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool plan_only,
+                        uint64_t max_cand_hint)
+{
+    DecArgs &a = c->dec;
+    cudaStream_t st = c->cur;
+    a.first = first;
+    a.out_base = out_base;
+    a.accept_1025 = (uint32_t)c->accept_1025;
+    a.count_only = plan_only ? 1u : 0u;
+
+    const uint64_t lim = a.length < a.avail ? a.length : a.avail;
+    const uint64_t span = lim > first ? lim - first : 0;
+    a.nchunks = (span + kFindChunk - 1) / kFindChunk;
+    if (!a.nchunks) a.nchunks = 1;
+    uint64_t max_cand = max_cand_hint ? max_cand_hint : span / 256 + 1024;
+    a.max_cand = max_cand;
+
+    size_t need = 0;
+    need += Arena::padded(a.nchunks * sizeof(uint32_t));
+    need += Arena::padded((a.nchunks + 1) * sizeof(uint64_t));
+    need += 4 * Arena::padded((max_cand + 1) * sizeof(uint64_t));
+    need += Arena::padded(max_cand * sizeof(uint32_t));
+    if (!c->dec_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
+    a.chunk_cnt = c->dec_ws.take<uint32_t>(a.nchunks);
+    a.chunk_off = c->dec_ws.take<uint64_t>(a.nchunks + 1);
+    a.cand = c->dec_ws.take<uint64_t>(max_cand + 1);
+    a.olen = c->dec_ws.take<uint64_t>(max_cand + 1);
+    a.out_off = c->dec_ws.take<uint64_t>(max_cand + 1);
+    a.end_off = c->dec_ws.take<uint64_t>(max_cand + 1);
+    a.blk_status = c->dec_ws.take<uint32_t>(max_cand);
+    a.result = c->d_result;
+
+    CU_TRY(cudaMemsetAsync(c->d_result, 0, 8 * sizeof(uint64_t), st));
+    const unsigned find_grid = (unsigned)((a.nchunks + kFindWarps - 1) / kFindWarps);
+    k_find<false><<<find_grid, kFindWarps * 32, 0, st>>>(a);
+    k_scan_chunks<<<1, kScanThreads, 0, st>>>(a);
+    k_find<true><<<find_grid, kFindWarps * 32, 0, st>>>(a);
+    k_gather<<<c->sm_count * 4, 256, 0, st>>>(a);
+    k_scan_olen<<<1, kScanThreads, 0, st>>>(a);
+    c->launches += 5;
+    if (!plan_only) {
+        // dynamic shared memory: output staging for one block (adapts to the stream's block size)
+        uint64_t want = c->dec_stage_want;
+        const uint64_t static_smem = sizeof(DecSmem) + 1024;
+        const uint64_t max_dyn = (uint64_t)c->max_smem_optin > static_smem
+                                     ? (uint64_t)c->max_smem_optin - static_smem : 16384;
+        if (want > max_dyn) want = max_dyn;
+        if (want < 16384) want = 16384;
+        want &= ~uint64_t(15);
+        if ((uint32_t)want != c->dec_stage) {
+            CU_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)want));
+            c->dec_stage = (uint32_t)want;
+        }
+        a.stage_cap = c->dec_stage;
+        int per_sm = 1;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode, kDecThreads,
+                                                             c->dec_stage));
+        if (per_sm < 1) per_sm = 1;
+        k_decode<<<c->sm_count * per_sm, kDecThreads, c->dec_stage, st>>>(a);
+        k_verify<<<1, kScanThreads, 0, st>>>(a);
+        c->launches += 2;
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_result, 8 * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, st));
+    if (plan_only) {
+        // total decoded size of the candidate chain = out_off[ncand]; fetched after the sync
+    }
+    return HUF_ERROR_SUCCESS;
+}
+
+}  // namespace
+
+huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                  uint64_t length, void *d_out, uint64_t out_capacity,
+                                  void *stream)
+{
+    if (!c || (!d_in && avail) || (!d_out && out_capacity)) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    DeviceGuard g(c->device);
+    if (!g.ok) return HUF_ERROR_FATAL;
+    c->cur = stream ? (cudaStream_t)stream : c->own_stream;
+    c->launches = 0;
+    c->dec_pending = true;
+    DecArgs &a = c->dec;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const uint8_t *>(d_in);
+    a.avail = avail;
+    a.length = length;
+    a.out = static_cast<uint8_t *>(d_out);
+    a.out_cap = out_capacity;
+    if (!length) return HUF_ERROR_SUCCESS;  // src/decoder.c:218: nothing to consume
+    return dec_enqueue(c, 0, 0, false, 0);
+}
+
+huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_t *consumed)
+{
+    if (!c || !out_len) return HUF_ERROR_INVALID_ARGUMENT;
+    if (!c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    c->dec_pending = false;
+    *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (!c->dec.length) return HUF_ERROR_SUCCESS;
+    DeviceGuard g(c->device);
+
+    for (;;) {
+        CU_TRY(cudaStreamSynchronize(c->cur));
+        const uint64_t *r = c->h_result;
+        if (r[6] > c->dec.max_cand) {
+            // candidate workspace too small for this stream: rerun the pass with the exact size
+            huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, r[6] + 16);
+            if (e != HUF_ERROR_SUCCESS) return e;
+            continue;
+        }
+        if (r[7] > c->dec_stage_want) c->dec_stage_want = r[7];  // adapt staging to block size
+        *out_len = r[4];
+        if (consumed) *consumed = r[3];
+        if (r[5]) return (huf_error_t)r[2];
+        // The speculative chain broke at a block boundary that no candidate marks (foreign
+        // header shape or a false positive): restart from the last proven position.
+        huf_error_t e = dec_enqueue(c, r[3], r[4], false, 0);
+        if (e != HUF_ERROR_SUCCESS) return e;
+    }
+}
+
+huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                 uint64_t length, uint64_t *out_len, uint64_t *nblocks,
+                                 void *stream)
+{
+    if (!c || !out_len || (!d_in && avail)) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    DeviceGuard g(c->device);
+    if (!g.ok) return HUF_ERROR_FATAL;
+    c->cur = stream ? (cudaStream_t)stream : c->own_stream;
+    c->launches = 0;
+    *out_len = 0;
+    if (nblocks) *nblocks = 0;
+    if (!length) return HUF_ERROR_SUCCESS;
+    DecArgs &a = c->dec;
+    memset(&a, 0, sizeof(a));
+    a.in = static_cast<const uint8_t *>(d_in);
+    a.avail = avail;
+    a.length = length;
+    uint64_t hint = 0;
+    for (;;) {
+        huf_error_t e = dec_enqueue(c, 0, 0, true, hint);
+        if (e != HUF_ERROR_SUCCESS) return e;
+        CU_TRY(cudaStreamSynchronize(c->cur));
+        if (c->h_result[6] > a.max_cand) {
+            hint = c->h_result[6] + 16;
+            continue;
+        }
+        break;
+    }
+    const uint64_t n = c->h_result[0];
+    uint64_t total = 0;
+    CU_TRY(cudaMemcpy(&total, a.out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *out_len = total;
+    if (nblocks) *nblocks = n;
+    if (c->h_result[7] > c->dec_stage_want) c->dec_stage_want = c->h_result[7];
+    return HUF_ERROR_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
+// raw device memory helpers
+// ------------------------------------------------------------------------------------------
+
+huf_error_t huf_b200_dev_alloc(void **d_ptr, uint64_t bytes)
+{
+    if (!d_ptr) return HUF_ERROR_INVALID_ARGUMENT;
+    CU_TRY(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_dev_free(void *d_ptr)
+{
+    CU_TRY(cudaFree(d_ptr));
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_copy_h2d(void *d_dst, const void *h_src, uint64_t bytes)
+{
+    if (bytes) CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
+{
+    if (bytes) CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return HUF_ERROR_SUCCESS;
+}
+
+}  // extern "C"
