@@ -2,7 +2,9 @@
 #pragma once
 
 #include <cstdint>
+#ifndef HUF_EMU  // tests/emu/cuda_emu.h stands in for the CUDA headers in the CPU test lane
 #include <cuda_runtime.h>
+#endif
 
 namespace hufb200 {
 
@@ -32,11 +34,15 @@ __device__ __forceinline__ int warp_in_cta() { return threadIdx.x >> 5; }
 // Streaming 16-byte load: read-only path, do not keep the line in L1.
 __device__ __forceinline__ uint4 ld_stream_u4(const void *p)
 {
+#ifdef HUF_EMU
+    return *reinterpret_cast<const uint4 *>(p);
+#else
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+#endif
 }
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }

@@ -386,7 +386,11 @@ __device__ __forceinline__ uint32_t decode_span(const DecSmem &sm, BitReader &br
 
 __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
 {
+#ifdef HUF_EMU
+    uint8_t *stage = hufemu::dyn_smem();
+#else
     extern __shared__ __align__(16) uint8_t stage[];
+#endif
     __shared__ DecSmem sm;
     const int tid = threadIdx.x;
     const uint64_t ncand = a.result[0];

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build(EncArgs a)
 #pragma unroll 1
             for (int s = 0; s < 2; s++) {
                 if (top == head) {  // front run used up: open the next one
-                    head = nxt;
+                    head = top = nxt;
                     if (head < made) {
                         const W rw = sm.iw[head];
                         uint32_t e = head + 1;

@@ -13,6 +13,11 @@
 
 using namespace hufb200;
 
+#ifndef HUF_EMU
+#define HUF_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace {
 
 constexpr uint32_t kSegMax = 16384;            // bytes per segment (u16 counters suffice)
@@ -280,14 +285,14 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
         const unsigned seg_grid = (unsigned)((nseg + kEncWarps - 1) / kEncWarps);
         const unsigned bld_grid = (unsigned)((a.npass + kBuildWarps - 1) / kBuildWarps);
 
-        k_seg_hist<<<seg_grid, kEncWarps * 32, 0, st>>>(a);
+        HUF_LAUNCH(k_seg_hist, seg_grid, kEncWarps * 32, 0, st, a);
         if (blocksize <= kW32MaxBlock)
-            k_build<uint32_t><<<bld_grid, kBuildWarps * 32, 0, st>>>(a);
+            HUF_LAUNCH(k_build<uint32_t>, bld_grid, kBuildWarps * 32, 0, st, a);
         else
-            k_build<uint64_t><<<bld_grid, kBuildWarps * 32, 0, st>>>(a);
-        k_scan_sizes<<<1, kScanThreads, 0, st>>>(a.blk_size + blk0, a.blk_off + blk0, a.npass,
-                                                 a.out_cap, a.status);
-        k_pack<<<seg_grid, kEncWarps * 32, 0, st>>>(a);
+            HUF_LAUNCH(k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, st, a);
+        HUF_LAUNCH(k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
+                   a.npass, a.out_cap, a.status);
+        HUF_LAUNCH(k_pack, seg_grid, kEncWarps * 32, 0, st, a);
         c->launches += 4;
     }
     CU_TRY(cudaGetLastError());
@@ -364,11 +369,11 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
 
     CU_TRY(cudaMemsetAsync(c->d_result, 0, 8 * sizeof(uint64_t), st));
     const unsigned find_grid = (unsigned)((a.nchunks + kFindWarps - 1) / kFindWarps);
-    k_find<false><<<find_grid, kFindWarps * 32, 0, st>>>(a);
-    k_scan_chunks<<<1, kScanThreads, 0, st>>>(a);
-    k_find<true><<<find_grid, kFindWarps * 32, 0, st>>>(a);
-    k_gather<<<c->sm_count * 4, 256, 0, st>>>(a);
-    k_scan_olen<<<1, kScanThreads, 0, st>>>(a);
+    HUF_LAUNCH(k_find<false>, find_grid, kFindWarps * 32, 0, st, a);
+    HUF_LAUNCH(k_scan_chunks, 1, kScanThreads, 0, st, a);
+    HUF_LAUNCH(k_find<true>, find_grid, kFindWarps * 32, 0, st, a);
+    HUF_LAUNCH(k_gather, c->sm_count * 4, 256, 0, st, a);
+    HUF_LAUNCH(k_scan_olen, 1, kScanThreads, 0, st, a);
     c->launches += 5;
     if (!plan_only) {
         // dynamic shared memory: output staging for one block (adapts to the stream's block size)
@@ -389,8 +394,8 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode, kDecThreads,
                                                              c->dec_stage));
         if (per_sm < 1) per_sm = 1;
-        k_decode<<<c->sm_count * per_sm, kDecThreads, c->dec_stage, st>>>(a);
-        k_verify<<<1, kScanThreads, 0, st>>>(a);
+        HUF_LAUNCH(k_decode, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
+        HUF_LAUNCH(k_verify, 1, kScanThreads, 0, st, a);
         c->launches += 2;
     }
     CU_TRY(cudaGetLastError());
