@@ -43,6 +43,9 @@ enum {
      * (src/encoder.c:270, src/tree.c:264).  Env var HUF_B200_ACCEPT_1025=1 sets the default
      * for contexts created afterwards (this is how huf_decode() is switched). */
     HUF_B200_OPT_ACCEPT_1025 = 1,
+    /* 1: bracket every kernel launch of the following *_async calls with CUDA events on the
+     * launching stream; read them with huf_b200_kernel_times after *_finish. */
+    HUF_B200_OPT_KERNEL_TIMING = 2,
 };
 
 /* Create a context on CUDA device `device` (< 0: the current device).  Fails with
@@ -92,6 +95,10 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *ctx, const void *d_in, uint64_t
 
 /* Counters for benches/tests: kernels launched by the last *_async call. */
 uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx);
+
+/* With HUF_B200_OPT_KERNEL_TIMING on: writes one "kernel_name milliseconds\n" line per launch
+ * of the last call into buf (NUL terminated). */
+huf_error_t huf_b200_kernel_times(huf_b200_ctx_t *ctx, char *buf, uint64_t buflen);
 
 /* Raw device memory helpers so that non-CUDA hosts (C, ctypes, cgo) can stage buffers
  * without linking the CUDA runtime themselves. */

@@ -175,6 +175,8 @@ class B200Lib(HuffmanCLib):
         d.huf_b200_decode_plan.argtypes = [vp, vp, u64, u64, C.POINTER(u64), C.POINTER(u64), vp]
         d.huf_b200_last_launch_count.restype = u64
         d.huf_b200_last_launch_count.argtypes = [vp]
+        d.huf_b200_kernel_times.argtypes = [vp, C.c_char_p, u64]
+        d.huf_b200_kernel_times.restype = C.c_int
         d.huf_b200_dev_alloc.argtypes = [C.POINTER(vp), u64]
         d.huf_b200_dev_free.argtypes = [vp]
         d.huf_b200_copy_h2d.argtypes = [vp, vp, u64]
@@ -249,3 +251,16 @@ class DeviceCodec:
 
     def launches(self) -> int:
         return self.lib.dll.huf_b200_last_launch_count(self.ctx)
+
+    def set_kernel_timing(self, on: bool) -> None:
+        self.lib.check(self.lib.dll.huf_b200_ctx_set_option(self.ctx, 2, int(on)), "set_option")
+
+    def kernel_times(self) -> list[tuple[str, float]]:
+        """(kernel name, milliseconds) per launch of the last call (needs set_kernel_timing)."""
+        buf = C.create_string_buffer(8192)
+        self.lib.check(self.lib.dll.huf_b200_kernel_times(self.ctx, buf, 8192), "huf_b200_kernel_times")
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit(" ", 1)
+            out.append((name, float(ms)))
+        return out

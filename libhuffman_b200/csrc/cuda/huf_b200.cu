@@ -18,6 +18,23 @@ using namespace hufb200;
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// Launch through the context: counts the launch and, when kernel timing is on, brackets it
+// with events on the launching stream.
+#define CTX_LAUNCH(c, kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                           \
+        huf_b200_ctx::Timed *t__ = nullptr;                                        \
+        if ((c)->timing && (c)->ntimed < 64) {                                     \
+            t__ = &(c)->timed[(c)->ntimed++];                                      \
+            t__->name = #kernel;                                                   \
+            cudaEventCreate(&t__->t0);                                             \
+            cudaEventCreate(&t__->t1);                                             \
+            cudaEventRecord(t__->t0, (stream));                                    \
+        }                                                                          \
+        HUF_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);                \
+        if (t__) cudaEventRecord(t__->t1, (stream));                               \
+        (c)->launches++;                                                           \
+    } while (0)
+
 namespace {
 
 constexpr uint32_t kSegMax = 16384;            // bytes per segment (u16 counters suffice)
@@ -70,6 +87,15 @@ struct huf_b200_ctx {
     uint64_t *h_result = nullptr;   // pinned mirror, [16]
     uint64_t launches = 0;
     int accept_1025 = 0;
+
+    // optional per-kernel timing (HUF_B200_OPT_KERNEL_TIMING): events around every launch
+    bool timing = false;
+    struct Timed {
+        const char *name;
+        cudaEvent_t t0, t1;
+    };
+    Timed timed[64];
+    int ntimed = 0;
 
     // encode call in flight
     bool enc_pending = false;
@@ -191,6 +217,9 @@ huf_error_t huf_b200_ctx_set_option(huf_b200_ctx_t *ctx, int option, int64_t val
     case HUF_B200_OPT_ACCEPT_1025:
         ctx->accept_1025 = value != 0;
         return HUF_ERROR_SUCCESS;
+    case HUF_B200_OPT_KERNEL_TIMING:
+        ctx->timing = value != 0;
+        return HUF_ERROR_SUCCESS;
     default:
         return HUF_ERROR_INVALID_ARGUMENT;
     }
@@ -213,6 +242,26 @@ uint64_t huf_b200_encode_bound(uint64_t length, uint64_t blocksize)
 
 uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
 
+huf_error_t huf_b200_kernel_times(huf_b200_ctx_t *c, char *buf, uint64_t buflen)
+{
+    if (!c || !buf || !buflen) return HUF_ERROR_INVALID_ARGUMENT;
+    DeviceGuard g(c->device);
+    size_t at = 0;
+    buf[0] = 0;
+    for (int i = 0; i < c->ntimed; i++) {
+        float ms = 0.f;
+        cudaEventSynchronize(c->timed[i].t1);
+        cudaEventElapsedTime(&ms, c->timed[i].t0, c->timed[i].t1);
+        cudaEventDestroy(c->timed[i].t0);
+        cudaEventDestroy(c->timed[i].t1);
+        int n = snprintf(buf + at, buflen - at, "%s %.6f\n", c->timed[i].name, (double)ms);
+        if (n < 0 || (size_t)n >= buflen - at) break;
+        at += (size_t)n;
+    }
+    c->ntimed = 0;
+    return HUF_ERROR_SUCCESS;
+}
+
 // ------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------
@@ -222,12 +271,13 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
                                   void *stream)
 {
     if (!c || (!d_in && length) || (!d_out && length)) return HUF_ERROR_INVALID_ARGUMENT;
-    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->own_stream;
     c->cur = st;
     c->launches = 0;
+    c->ntimed = 0;
     if (!blocksize) blocksize = length;
 
     const uint64_t nblocks = huf_b200_block_count(length, blocksize);
@@ -285,15 +335,14 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
         const unsigned seg_grid = (unsigned)((nseg + kEncWarps - 1) / kEncWarps);
         const unsigned bld_grid = (unsigned)((a.npass + kBuildWarps - 1) / kBuildWarps);
 
-        HUF_LAUNCH(k_seg_hist, seg_grid, kEncWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_seg_hist, seg_grid, kEncWarps * 32, 0, st, a);
         if (blocksize <= kW32MaxBlock)
-            HUF_LAUNCH(k_build<uint32_t>, bld_grid, kBuildWarps * 32, 0, st, a);
+            CTX_LAUNCH(c, k_build<uint32_t>, bld_grid, kBuildWarps * 32, 0, st, a);
         else
-            HUF_LAUNCH(k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, st, a);
-        HUF_LAUNCH(k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
+            CTX_LAUNCH(c, k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
                    a.npass, a.out_cap, a.status);
-        HUF_LAUNCH(k_pack, seg_grid, kEncWarps * 32, 0, st, a);
-        c->launches += 4;
+        CTX_LAUNCH(c, k_pack, seg_grid, kEncWarps * 32, 0, st, a);
     }
     CU_TRY(cudaGetLastError());
     // result: total size + status, copied to the pinned mirror on the same stream
@@ -369,12 +418,11 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
 
     CU_TRY(cudaMemsetAsync(c->d_result, 0, 8 * sizeof(uint64_t), st));
     const unsigned find_grid = (unsigned)((a.nchunks + kFindWarps - 1) / kFindWarps);
-    HUF_LAUNCH(k_find<false>, find_grid, kFindWarps * 32, 0, st, a);
-    HUF_LAUNCH(k_scan_chunks, 1, kScanThreads, 0, st, a);
-    HUF_LAUNCH(k_find<true>, find_grid, kFindWarps * 32, 0, st, a);
-    HUF_LAUNCH(k_gather, c->sm_count * 4, 256, 0, st, a);
-    HUF_LAUNCH(k_scan_olen, 1, kScanThreads, 0, st, a);
-    c->launches += 5;
+    CTX_LAUNCH(c, k_find<false>, find_grid, kFindWarps * 32, 0, st, a);
+    CTX_LAUNCH(c, k_scan_chunks, 1, kScanThreads, 0, st, a);
+    CTX_LAUNCH(c, k_find<true>, find_grid, kFindWarps * 32, 0, st, a);
+    CTX_LAUNCH(c, k_gather, c->sm_count * 4, 256, 0, st, a);
+    CTX_LAUNCH(c, k_scan_olen, 1, kScanThreads, 0, st, a);
     if (!plan_only) {
         // dynamic shared memory: output staging for one block (adapts to the stream's block size)
         uint64_t want = c->dec_stage_want;
@@ -394,9 +442,8 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode, kDecThreads,
                                                              c->dec_stage));
         if (per_sm < 1) per_sm = 1;
-        HUF_LAUNCH(k_decode, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
-        HUF_LAUNCH(k_verify, 1, kScanThreads, 0, st, a);
-        c->launches += 2;
+        CTX_LAUNCH(c, k_decode, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
+        CTX_LAUNCH(c, k_verify, 1, kScanThreads, 0, st, a);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(c->h_result, c->d_result, 8 * sizeof(uint64_t),
@@ -414,11 +461,12 @@ huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
                                   void *stream)
 {
     if (!c || (!d_in && avail) || (!d_out && out_capacity)) return HUF_ERROR_INVALID_ARGUMENT;
-    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
     c->cur = stream ? (cudaStream_t)stream : c->own_stream;
     c->launches = 0;
+    c->ntimed = 0;
     c->dec_pending = true;
     DecArgs &a = c->dec;
     memset(&a, 0, sizeof(a));

@@ -22,9 +22,10 @@ _ref = None
 
 def build(ref_root: str = "/root/reference") -> None:
     """Compile the oracle and, when the reference tree is present, oracle/_ref."""
-    subprocess.run(["make", "-s", "-C", str(HERE), "oracle"], check=True)
+    quiet = {"stdout": subprocess.DEVNULL}
+    subprocess.run(["make", "-s", "-C", str(HERE), "oracle"], check=True, **quiet)
     if Path(ref_root, "src").is_dir():
-        subprocess.run(["make", "-s", "-C", str(HERE), "ref", f"REF={ref_root}"], check=True)
+        subprocess.run(["make", "-s", "-C", str(HERE), "ref", f"REF={ref_root}"], check=True, **quiet)
 
 
 def _lib():
