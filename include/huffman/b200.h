@@ -35,6 +35,12 @@ extern "C" {
 
 typedef struct huf_b200_ctx huf_b200_ctx_t;
 
+/* `stream` arguments take a cudaStream_t handle.  NULL is CUDA's default stream (the value
+ * torch.cuda.current_stream().cuda_stream has unless a side stream is active);
+ * HUF_B200_STREAM_PRIVATE selects the context's own non-blocking stream (what the host layer
+ * uses so that huf_encode/huf_decode never serialise with an application's other streams). */
+#define HUF_B200_STREAM_PRIVATE ((void *)(intptr_t)-1)
+
 /* Options for huf_b200_ctx_set_option. */
 enum {
     /* 0 (default): tree_len > HUF_BTREE_LEN is HUF_ERROR_BTREE_OVERFLOW exactly like the

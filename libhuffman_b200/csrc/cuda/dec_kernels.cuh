@@ -23,7 +23,7 @@
 namespace hufb200 {
 
 constexpr int kFindWarps = 8;
-constexpr uint32_t kFindChunk = 4096;  // bytes scanned per warp
+constexpr uint32_t kFindChunk = 32768;  // bytes scanned per warp
 constexpr int kDecThreads = 256;
 constexpr int kLutBits = 12;
 constexpr int kLutSize = 1 << kLutBits;
@@ -113,15 +113,34 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
     uint32_t total = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
-    for (uint32_t it = 0; it < kFindChunk / 512; it++) {
-        const uint64_t o0 = c0 + it * 512 + lane * 16;  // this lane tests offsets o0 .. o0+15
-        uint32_t mask = 0;                              // bit i: offset o0+i is a candidate
+    const uint64_t in_aligned = a.avail & ~uint64_t(15);  // bytes readable with 16-byte loads
+    for (uint32_t it0 = 0; it0 < kFindChunk / 512; it0 += 4) {
+        if (c0 + (uint64_t)it0 * 512 >= lim) break;  // warp-uniform: nothing left in this chunk
+        // four independent 16-byte loads in flight per lane
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (vec_ok && (c0 & 15) == 0 && o0 + 16 <= in_aligned) v[u] = ld_stream_u4(a.in + o0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+        const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;  // offsets o0 .. o0+15
+        uint32_t mask = 0;                                               // bit i: o0+i is a candidate
+        // the 16 bytes that follow come from the next lane; lane 31 fetches them itself
+        uint32_t n0 = __shfl_down_sync(kFull, v[u].x, 1);
+        uint32_t n1 = __shfl_down_sync(kFull, v[u].y, 1);
+        uint32_t n2 = __shfl_down_sync(kFull, v[u].z, 1);
+        const bool fast = vec_ok && (c0 & 15) == 0 && o0 + 32 <= in_aligned;
+        if (lane == 31 && fast) {
+            const uint4 nx = ld_stream_u4(a.in + o0 + 16);
+            n0 = nx.x; n1 = nx.y; n2 = nx.z;
+        }
         if (o0 < lim) {
             // bytes o0+11 .. o0+26 decide the pre-filter
-            if (vec_ok && (o0 & 15) == 0 && o0 + 32 <= a.avail) {
-                const uint4 v0 = ld_stream_u4(a.in + o0);
-                const uint4 v1 = ld_stream_u4(a.in + o0 + 16);
-                const uint32_t d[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if (fast) {
+                const uint32_t d[8] = {v[u].x, v[u].y, v[u].z, v[u].w, n0, n1, n2, 0u};
                 uint32_t pre = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -161,6 +180,7 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
             }
             wr += __shfl_sync(kFull, incl, 31);
         }
+        }  // u
     }
     if (!EMIT) {
         total = warp_sum(total);
@@ -248,28 +268,38 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_olen(DecArgs a)
 // K5: block decode.
 // ------------------------------------------------------------------------------------------
 
+constexpr int kMaxElems = 1040;   // serialised tree elements (<= 1025) padded
+
 struct DecSmem {
-    int16_t elems[kMaxNodes + 6];   // serialised tree as read from the stream
-    int16_t lch[kMaxNodes];         // child node ids, -1 = absent
-    int16_t rch[kMaxNodes];
-    int16_t label[kMaxNodes];
+    int16_t elems[kMaxElems];    // serialised tree as read from the stream; node id == element index
+    int16_t open[kMaxElems];     // open child slots before element i is consumed (1 for i == 0)
+    int16_t lch[kMaxElems];      // child node ids, -1 = absent
+    int16_t rch[kMaxElems];
+    int16_t rraw[kMaxElems];     // element index that fills the right slot (-1: elements ran out)
+    uint16_t pre[kMaxElems];     // code prefix (depth bits) of nodes at depth <= kLutBits
+    uint8_t lvl[kMaxElems];      // depth of the node, 0xff = deeper than the table or unused
     uint16_t lut[kLutSize];
-    // terminals of the depth-limited tree, in pre-order == ascending code order
-    uint16_t t_start[kMaxNodes * 2 + 4];  // first LUT index covered
-    uint16_t t_entry[kMaxNodes * 2 + 4];
-    uint8_t t_depth[kMaxNodes * 2 + 4];
     uint32_t sub_end[kDecThreads + 1];
     uint32_t warp_tot[kDecThreads / 32];
     uint32_t n_term;
+    uint32_t n_wide;
+    uint32_t n_eff;              // elements that belong to the tree
     int32_t root;
     uint32_t hdr_status;
     uint32_t tree_len;
     uint64_t orig_len;
     uint32_t err_pos;     // smallest payload bit position at which the true chain failed
-    uint32_t err_code;
     uint32_t end_bit;
-    uint32_t changed;
     uint64_t total_syms;
+};
+
+// Terminals of the depth-limited tree (leaf, absent child, or inner node at table depth) are
+// collected in the dynamic shared memory area, which is free until the decode phases start.
+struct Terminal {
+    uint16_t start;   // first LUT index covered
+    uint16_t entry;
+    uint16_t depth;
+    uint16_t pad;
 };
 
 // MSB-first bit window over the payload, addressed in payload-relative bit positions.
@@ -351,7 +381,7 @@ __device__ __forceinline__ int decode_one(const DecSmem &sm, BitReader &br, uint
         br.skip(1);
         pos += 1;
         node = nx;
-        if (sm.lch[node] < 0 && sm.rch[node] < 0) return (uint8_t)sm.label[node];
+        if (sm.lch[node] < 0 && sm.rch[node] < 0) return (uint8_t)sm.elems[node];
     }
 }
 
@@ -424,10 +454,12 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             sm.orig_len = ol;
             sm.tree_len = tl;
             sm.err_pos = 0xffffffffu;
-            sm.err_code = kOk;
             sm.end_bit = 0;
             sm.n_term = 0;
+            sm.n_wide = 0;
+            sm.n_eff = tl;
             sm.root = -1;
+            sm.total_syms = 0;
         }
         __syncthreads();
         if (sm.hdr_status != kOk) {
@@ -440,124 +472,144 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         const uint32_t tl = sm.tree_len;
         const uint64_t orig_len = sm.orig_len;
         const uint64_t pay0 = off + kHdrFixed + 2ull * tl;
-        for (uint32_t i = tid; i < tl; i += kDecThreads)
-            sm.elems[i] = (int16_t)rd_u16(a.in + off + kHdrFixed + 2ull * i);
+
+        // ---- tree -> node arrays, in parallel (grammar of src/tree.c:138-208: T := -1 | v T T,
+        // missing elements = absent children, trailing elements ignored).
+        // open[i] = child slots still open before element i is consumed: a node consumes one
+        // and opens two, an absent marker consumes one.  The tree ends where open hits 0.
+        constexpr int kPer = (kMaxElems + kDecThreads - 1) / kDecThreads;  // 5 elements per thread
+        {
+            int v[kPer];
+            int sum = 0;
+#pragma unroll
+            for (int q = 0; q < kPer; q++) {
+                const uint32_t i = tid * kPer + q;
+                int e = -1;
+                if (i < tl) {
+                    e = (int16_t)rd_u16(a.in + off + kHdrFixed + 2ull * i);
+                    sm.elems[i] = (int16_t)e;
+                }
+                v[q] = i < tl ? (e != -1 ? 1 : -1) : 0;
+                sum += v[q];
+            }
+            int incl = warp_incl_scan(sum);
+            if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = (uint32_t)incl;
+            __syncthreads();
+            if (tid < 32) {
+                const int t = tid < kDecThreads / 32 ? (int)sm.warp_tot[tid] : 0;
+                const int ti = warp_incl_scan(t);
+                if (tid < kDecThreads / 32) sm.warp_tot[tid] = (uint32_t)(ti - t);
+            }
+            __syncthreads();
+            int run = 1 + (int)sm.warp_tot[tid >> 5] + incl - sum;
+#pragma unroll
+            for (int q = 0; q < kPer; q++) {
+                const uint32_t i = tid * kPer + q;
+                if (i < tl) {
+                    sm.open[i] = (int16_t)run;
+                    if (run == 0) atomicMin(&sm.n_eff, i);
+                    sm.lvl[i] = 0xff;
+                }
+                run += v[q];
+            }
+        }
         for (uint32_t i = tid; i < kLutSize; i += kDecThreads) sm.lut[i] = kLutDead | 1;
         __syncthreads();
+        const uint32_t n_eff = sm.n_eff;
 
-        // ---- tree -> node arrays + terminal list (grammar of src/tree.c:138-208)
-        // One pass with a stack of open child slots: every element fills the top slot; a
-        // node opens two more (left on top).  Elements that run out leave slots absent;
-        // trailing elements are ignored.
-        if (tid == 0) {
-            // slot stack entries: parent node id (or -1 for the root slot) | side << 15,
-            // plus the code prefix (first kLutBits bits) and depth of the slot.
-            // Stored in the staging area's first bytes (not yet in use).
-            uint32_t *stk = reinterpret_cast<uint32_t *>(stage);  // {parent|side, prefix|depth<<16}
-            int sp = 0;
-            uint32_t nodes = 0, nt = 0;
-            stk[0] = 0xffffffffu;
-            stk[1] = 0;  // prefix 0, depth 0
-            sp = 1;
-            uint32_t pos = 0;
-            while (sp > 0) {
-                sp--;
-                const uint32_t who = stk[2 * sp];
-                const uint32_t pd = stk[2 * sp + 1];
-                const uint32_t depth = pd >> 16;
-                const uint32_t prefix = pd & 0xffffu;  // depth (<= kLutBits) leading bits
-                int16_t v = -1;
-                if (pos < tl) v = sm.elems[pos++];
-                int id = -1;
-                if (v != -1) {
-                    id = (int)nodes++;
-                    sm.label[id] = v;
-                    sm.lch[id] = -1;
-                    sm.rch[id] = -1;
+        // children: left slot is filled by the next element; the right slot by the first later
+        // element that sees the same number of open slots as this node did.
+        for (uint32_t i = tid; i < n_eff; i += kDecThreads) {
+            int l = -1, r = -1, rr = -1;
+            if (sm.elems[i] != -1) {
+                if (i + 1 < n_eff && sm.elems[i + 1] != -1) l = (int)(i + 1);
+                const int want = sm.open[i];
+                uint32_t k = i + 2;
+                while (k < n_eff && sm.open[k] > want) k++;
+                if (k < n_eff && i + 1 < n_eff) {
+                    rr = (int)k;
+                    if (sm.elems[k] != -1) r = (int)k;
                 }
-                if (who == 0xffffffffu) {
-                    sm.root = id;
-                } else if (id >= 0) {
-                    if (who & 0x8000u) sm.rch[who & 0x7fffu] = (int16_t)id;
-                    else sm.lch[who & 0x7fffu] = (int16_t)id;
-                }
-                if (id < 0) {
-                    // absent child: consuming the bit that leads here kills the walk
-                    if (depth >= 1 && depth <= (uint32_t)kLutBits) {
-                        sm.t_start[nt] = (uint16_t)(prefix << (kLutBits - depth));
-                        sm.t_depth[nt] = (uint8_t)depth;
-                        sm.t_entry[nt] = (uint16_t)(kLutDead | depth);
-                        nt++;
-                    }
-                    continue;
-                }
-                // a node with two absent children is a leaf; that is only known after its
-                // two slots were filled, so terminals for real nodes are emitted below by
-                // looking one/two elements ahead.
-                const bool l_absent = !(pos < tl) || sm.elems[pos] == -1;
-                bool leaf = false;
-                if (l_absent) {
-                    const bool r_absent = !(pos + 1 < tl) || sm.elems[pos + 1] == -1;
-                    leaf = r_absent;
-                }
-                if (leaf && depth >= 1) {
-                    // consume its two absent slots right here
-                    if (pos < tl) pos++;
-                    if (pos < tl) pos++;
-                    if (depth <= (uint32_t)kLutBits) {
-                        sm.t_start[nt] = (uint16_t)(prefix << (kLutBits - depth));
-                        sm.t_depth[nt] = (uint8_t)depth;
-                        sm.t_entry[nt] = (uint16_t)((depth << 8) | (uint8_t)v);
-                        nt++;
-                    }
-                    continue;
-                }
-                if (leaf && depth == 0) {
-                    // root without children: every first bit walks into an absent child
-                    if (pos < tl) pos++;
-                    if (pos < tl) pos++;
-                    continue;  // LUT stays all-DEAD(depth 1)
-                }
-                if (depth == (uint32_t)kLutBits) {
-                    // inner node exactly at the table depth: long-code continuation
-                    sm.t_start[nt] = (uint16_t)prefix;
-                    sm.t_depth[nt] = (uint8_t)depth;
-                    sm.t_entry[nt] = (uint16_t)(kLutLong | id);
-                    nt++;
-                }
-                const uint32_t cd = depth + 1;
-                const uint32_t cp = cd <= (uint32_t)kLutBits ? (prefix << 1) : prefix;
-                // right slot below, left slot on top
-                stk[2 * sp] = (uint32_t)id | 0x8000u;
-                stk[2 * sp + 1] = (cd << 16) | (cd <= (uint32_t)kLutBits ? (cp | 1u) : cp);
-                sp++;
-                stk[2 * sp] = (uint32_t)id;
-                stk[2 * sp + 1] = (cd << 16) | cp;
-                sp++;
             }
-            sm.n_term = nt;
+            sm.lch[i] = (int16_t)l;
+            sm.rch[i] = (int16_t)r;
+            sm.rraw[i] = (int16_t)rr;
+        }
+        if (tid == 0 && n_eff > 0 && sm.elems[0] != -1) {
+            sm.root = 0;
+            sm.lvl[0] = 0;
+            sm.pre[0] = 0;
         }
         __syncthreads();
+
+        // depth-limited expansion, one level per round: leaves and absent children become
+        // table terminals, inner nodes at the table depth become long-code continuations.
+        Terminal *term = reinterpret_cast<Terminal *>(stage);
+        uint16_t *wide = reinterpret_cast<uint16_t *>(stage + sizeof(Terminal) * (2 * kMaxElems + 8));
+        for (uint32_t d = 0; d <= (uint32_t)kLutBits; d++) {
+            for (uint32_t i = tid; i < n_eff; i += kDecThreads) {
+                if (sm.lvl[i] != d) continue;
+                const uint32_t p = sm.pre[i];
+                const int l = sm.lch[i], r = sm.rch[i];
+                const bool leaf = l < 0 && r < 0;
+                uint32_t n_new = 0;
+                Terminal t[2];
+                if (leaf) {
+                    if (d >= 1) {
+                        t[0].start = (uint16_t)(p << (kLutBits - d));
+                        t[0].entry = (uint16_t)((d << 8) | (uint8_t)sm.elems[i]);
+                        t[0].depth = (uint16_t)d;
+                        n_new = 1;
+                    }  // a root without children keeps the all-dead table
+                } else if (d == (uint32_t)kLutBits) {
+                    t[0].start = (uint16_t)p;
+                    t[0].entry = (uint16_t)(kLutLong | i);
+                    t[0].depth = (uint16_t)d;
+                    n_new = 1;
+                } else {
+                    const int kids[2] = {l, r};
+#pragma unroll
+                    for (int side = 0; side < 2; side++) {
+                        const uint32_t cp = (p << 1) | (uint32_t)side;
+                        if (kids[side] >= 0) {
+                            sm.lvl[kids[side]] = (uint8_t)(d + 1);
+                            sm.pre[kids[side]] = (uint16_t)cp;
+                        } else {
+                            // consuming this bit walks into an absent child
+                            t[n_new].start = (uint16_t)(cp << (kLutBits - d - 1));
+                            t[n_new].entry = (uint16_t)(kLutDead | (d + 1));
+                            t[n_new].depth = (uint16_t)(d + 1);
+                            n_new++;
+                        }
+                    }
+                }
+                if (n_new) {
+                    const uint32_t at = atomicAdd(&sm.n_term, n_new);
+                    for (uint32_t q = 0; q < n_new; q++) {
+                        term[at + q] = t[q];
+                        if (t[q].depth < (uint32_t)kLutBits - 6) wide[atomicAdd(&sm.n_wide, 1u)] = (uint16_t)(at + q);
+                    }
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- fill the lookup table from the terminal list (ranges are disjoint)
         {
             const uint32_t nt = sm.n_term;
             for (uint32_t t = tid; t < nt; t += kDecThreads) {
-                const uint32_t span = 1u << (kLutBits - sm.t_depth[t]);
+                const Terminal tm = term[t];
+                const uint32_t span = 1u << (kLutBits - tm.depth);
                 if (span <= 64) {
-                    const uint32_t s0 = sm.t_start[t];
-                    const uint16_t e = sm.t_entry[t];
-                    for (uint32_t i = 0; i < span; i++) sm.lut[s0 + i] = e;
+                    for (uint32_t i = 0; i < span; i++) sm.lut[tm.start + i] = tm.entry;
                 }
             }
             // wide ranges (depth <= 5, at most 63 of them): all threads cooperate
-            for (uint32_t t = 0; t < nt; t++) {
-                const uint32_t d = sm.t_depth[t];
-                if (d >= (uint32_t)kLutBits - 6) continue;
-                const uint32_t span = 1u << (kLutBits - d);
-                const uint32_t s0 = sm.t_start[t];
-                const uint16_t e = sm.t_entry[t];
-                for (uint32_t i = tid; i < span; i += kDecThreads) sm.lut[s0 + i] = e;
+            const uint32_t nw = sm.n_wide;
+            for (uint32_t w = 0; w < nw; w++) {
+                const Terminal tm = term[wide[w]];
+                const uint32_t span = 1u << (kLutBits - tm.depth);
+                for (uint32_t i = tid; i < span; i += kDecThreads) sm.lut[tm.start + i] = tm.entry;
             }
         }
         __syncthreads();
@@ -577,11 +629,16 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             }
             continue;
         }
-        const uint64_t pay_room_bits = 8ull * (a.avail - pay0);
-        const bool doomed = orig_len > pay_room_bits;  // cannot finish: error is EOF or dead walk
-        if (pay_room_bits >= 0xfffffff0ull || (!doomed && orig_len >= 0xfffffff0ull)) {
+        // Bit positions inside a block are 32-bit.  The readable room behind the header is
+        // clipped accordingly; a block that really needs more than ~512 MiB of payload is
+        // refused (HUF_ERROR_FATAL) instead of being mis-decoded.
+        const uint64_t pay_room_full = 8ull * (a.avail - pay0);
+        const bool room_clipped = pay_room_full > 0xffffff00ull;
+        const uint64_t pay_room_bits = room_clipped ? 0xffffff00ull : pay_room_full;
+        const bool doomed = orig_len > pay_room_full;  // cannot finish: error is EOF or dead walk
+        if (!doomed && orig_len >= 0xfffffff0ull) {
             if (tid == 0) {
-                a.blk_status[j] = kErrFatal;  // block too large for this kernel
+                a.blk_status[j] = kErrFatal;
                 a.end_off[j] = pay0;
             }
             continue;
@@ -590,7 +647,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         // ---- sub-block split over the guessed payload extent
         uint64_t guess_bytes = next_cand > pay0 ? next_cand - pay0 : 0;
         if (guess_bytes > a.avail - pay0) guess_bytes = a.avail - pay0;
-        const uint32_t guess_bits = (uint32_t)(8 * guess_bytes);
+        const uint32_t guess_bits = (uint32_t)min(8 * guess_bytes, pay_room_bits);
         const uint32_t room_bits = (uint32_t)pay_room_bits;
         uint32_t sub = (guess_bits + kDecThreads - 1) / kDecThreads;
         sub = (sub + 31u) & ~31u;
@@ -697,9 +754,10 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         // of readable bytes first is READ_WRITE (src/decoder.c:53,69-71).
         uint32_t status = kOk;
         if (sm.err_pos != 0xffffffffu) {
-            status = sm.err_pos >= room_bits ? kErrIO : kErrCorrupt;
+            status = sm.err_pos >= room_bits ? (room_clipped ? kErrFatal : kErrIO) : kErrCorrupt;
         } else if (sm.end_bit > room_bits) {
-            status = kErrIO;  // the finishing code word extends past the readable bytes
+            // the finishing code word extends past the readable bytes
+            status = room_clipped ? kErrFatal : kErrIO;
         }
 
         // ---- output: staged blocks leave through coalesced 16-byte stores

@@ -138,6 +138,11 @@ struct DeviceGuard {
     }
 };
 
+cudaStream_t pick_stream(huf_b200_ctx *c, void *stream)
+{
+    return stream == HUF_B200_STREAM_PRIVATE ? c->own_stream : (cudaStream_t)stream;
+}
+
 uint32_t pick_seg(uint64_t blocksize)
 {
     uint64_t s = blocksize < kSegMax ? blocksize : kSegMax;
@@ -274,7 +279,7 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     if (c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->own_stream;
+    cudaStream_t st = pick_stream(c, stream);
     c->cur = st;
     c->launches = 0;
     c->ntimed = 0;
@@ -428,9 +433,9 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         uint64_t want = c->dec_stage_want;
         const uint64_t static_smem = sizeof(DecSmem) + 1024;
         const uint64_t max_dyn = (uint64_t)c->max_smem_optin > static_smem
-                                     ? (uint64_t)c->max_smem_optin - static_smem : 16384;
+                                     ? (uint64_t)c->max_smem_optin - static_smem : 20480;
         if (want > max_dyn) want = max_dyn;
-        if (want < 16384) want = 16384;
+        if (want < 20480) want = 20480;  // the terminal list of the table build lives here
         want &= ~uint64_t(15);
         if ((uint32_t)want != c->dec_stage) {
             CU_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -464,7 +469,7 @@ huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     if (c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
-    c->cur = stream ? (cudaStream_t)stream : c->own_stream;
+    c->cur = pick_stream(c, stream);
     c->launches = 0;
     c->ntimed = 0;
     c->dec_pending = true;
@@ -517,7 +522,7 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
     if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
-    c->cur = stream ? (cudaStream_t)stream : c->own_stream;
+    c->cur = pick_stream(c, stream);
     c->launches = 0;
     *out_len = 0;
     if (nblocks) *nblocks = 0;

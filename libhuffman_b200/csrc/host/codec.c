@@ -222,7 +222,7 @@ encode_locked(huf_b200_ctx_t *ctx, const huf_config_t *cfg)
             }
             if (err == HUF_ERROR_SUCCESS) {
                 err = huf_b200_encode_async(ctx, g_dev.in, usable, blocksize, g_dev.out,
-                                            g_dev.out_cap, NULL);
+                                            g_dev.out_cap, HUF_B200_STREAM_PRIVATE);
             }
             if (err == HUF_ERROR_SUCCESS) {
                 err = huf_b200_encode_finish(ctx, &out_len);
@@ -296,14 +296,15 @@ decode_locked(huf_b200_ctx_t *ctx, const huf_config_t *cfg)
             err = huf_b200_copy_h2d(g_dev.in, data + done_in, in_now);
         }
         if (err == HUF_ERROR_SUCCESS) {
-            err = huf_b200_decode_plan(ctx, g_dev.in, in_now, len_now, &est, NULL, NULL);
+            err = huf_b200_decode_plan(ctx, g_dev.in, in_now, len_now, &est, NULL,
+                                       HUF_B200_STREAM_PRIVATE);
         }
         if (err == HUF_ERROR_SUCCESS) {
             err = dev_reserve(&g_dev.out, &g_dev.out_cap, est + 16);
         }
         if (err == HUF_ERROR_SUCCESS) {
             err = huf_b200_decode_async(ctx, g_dev.in, in_now, len_now, g_dev.out, g_dev.out_cap,
-                                        NULL);
+                                        HUF_B200_STREAM_PRIVATE);
         }
         if (err != HUF_ERROR_SUCCESS) {
             break;

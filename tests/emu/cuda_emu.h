@@ -261,6 +261,12 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d)
     return hufemu::warp_exchange(v, [&](uint64_t *x) { return l >= d ? hufemu::from_bits<T>(x[l - d]) : v; });
 }
 template <typename T>
+inline T __shfl_down_sync(unsigned, T v, unsigned d)
+{
+    const unsigned l = hufemu::lane();
+    return hufemu::warp_exchange(v, [&](uint64_t *x) { return l + d < 32 ? hufemu::from_bits<T>(x[l + d]) : v; });
+}
+template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int d)
 {
     const unsigned l = hufemu::lane();
