@@ -48,6 +48,7 @@ struct DecArgs {
     uint32_t stage_cap;  // bytes of dynamic shared memory usable as output staging
     // workspace
     uint32_t *chunk_cnt;   // [nchunks]
+    uint32_t *slots;       // [nchunks][kFindSlots] chunk-relative candidate offsets (sparse mode)
     uint64_t *chunk_off;   // [nchunks + 1]
     uint64_t *cand;        // [max_cand]  candidate byte offsets, ascending
     uint64_t *olen;        // [max_cand]  orig_len per candidate
@@ -59,6 +60,7 @@ struct DecArgs {
     uint64_t *result;      // [0] ncand [1] proven blocks [2] status [3] consumed [4] out bytes
                            // [5] chain complete flag [6] candidates found (may exceed max_cand)
                            // [7] largest orig_len among the candidates
+                           // [8] sparse-mode slot overflow (rerun with the two-pass scan)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -99,17 +101,24 @@ __device__ __forceinline__ bool header_plausible(const DecArgs &a, uint64_t off)
 // Pre-filter: byte at offset+11 (high byte of tree[0] = 255+n, n in 1..256) must be 0x01.
 // ------------------------------------------------------------------------------------------
 
-template <bool EMIT>
+// MODE 0: count per chunk.  MODE 1: ordered emit into cand[] (after the chunk scan).
+// MODE 2: single pass for sparse streams: count and park up to kFindSlots candidates per chunk
+// in a slot array (k_compact moves them into cand[]); denser chunks raise result[8] and the
+// host reruns with the exact two-pass scheme (MODE 0 + MODE 1).
+constexpr uint32_t kFindSlots = 8;
+
+template <int MODE>
 __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
 {
+    constexpr bool EMIT = MODE != 0;
     const int lane = lane_id();
     const uint64_t chunk = (uint64_t)blockIdx.x * kFindWarps + warp_in_cta();
     if (chunk >= a.nchunks) return;
     const uint64_t lim = a.length < a.avail ? a.length : a.avail;  // starts must be < lim
     const uint64_t c0 = a.first + chunk * kFindChunk;
-    if (EMIT && a.chunk_cnt[chunk] == 0) return;
+    if (MODE == 1 && a.chunk_cnt[chunk] == 0) return;
 
-    uint64_t wr = EMIT ? a.chunk_off[chunk] : 0;
+    uint64_t wr = MODE == 1 ? a.chunk_off[chunk] : 0;
     uint32_t total = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
@@ -165,9 +174,8 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
             if (o0 == a.first) mask |= 1u;  // the proven start is always block 0
         }
         const uint32_t n = __popc(mask);
-        if (!EMIT) {
-            total += n;
-        } else {
+        total += n;
+        if (EMIT) {
             // ordered emit: lanes in order, offsets in order inside a lane
             const uint32_t incl = warp_incl_scan(n);
             uint64_t at = wr + incl - n;
@@ -175,16 +183,36 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
             while (m) {
                 const int i = __ffs(m) - 1;
                 m &= m - 1;
-                if (at < a.max_cand) a.cand[at] = o0 + i;
+                if (MODE == 1) {
+                    if (at < a.max_cand) a.cand[at] = o0 + i;
+                } else if (at < kFindSlots) {
+                    a.slots[chunk * kFindSlots + at] = (uint32_t)(o0 + i - c0);
+                }
                 at++;
             }
             wr += __shfl_sync(kFull, incl, 31);
         }
         }  // u
     }
-    if (!EMIT) {
+    if (MODE != 1) {
         total = warp_sum(total);
-        if (lane == 0) a.chunk_cnt[chunk] = total;
+        if (lane == 0) {
+            a.chunk_cnt[chunk] = total;
+            if (MODE == 2 && total > kFindSlots) a.result[8] = 1;
+        }
+    }
+}
+
+// MODE 2 follow-up: slots -> cand[], in stream order.
+__global__ void k_compact(DecArgs a)
+{
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= a.nchunks) return;
+    const uint32_t n = min(a.chunk_cnt[chunk], kFindSlots);
+    const uint64_t at = a.chunk_off[chunk];
+    const uint64_t c0 = a.first + chunk * kFindChunk;
+    for (uint32_t i = 0; i < n; i++) {
+        if (at + i < a.max_cand) a.cand[at + i] = c0 + a.slots[chunk * kFindSlots + i];
     }
 }
 
@@ -303,33 +331,56 @@ struct Terminal {
 };
 
 // MSB-first bit window over the payload, addressed in payload-relative bit positions.
+// The stream is fetched in 16-byte chunks with one chunk prefetched ahead, so that the global
+// load latency is off the per-symbol dependency chain; bytes past `avail` read as zero.
 struct BitReader {
     const uint8_t *in;
-    uint64_t avail;     // readable bytes of the whole stream
-    uint64_t base_bit;  // global bit position of payload bit 0
-    uint64_t buf;       // next bits, left aligned
-    int have;           // valid bits in buf
-    uint64_t next_word; // index of the next aligned 32-bit word to append
+    uint64_t avail;      // readable bytes of the whole stream
+    uint64_t base_bit;   // global bit position of payload bit 0
+    uint64_t buf;        // next bits, left aligned
+    int have;            // valid bits in buf
+    uint4 cur, nxt;      // chunk being consumed and the prefetched one
+    uint64_t chunk;      // index of `cur`
+    int k;               // next 32-bit word of `cur` to append
+    bool vec;            // stream base is 16-byte aligned
 
-    __device__ __forceinline__ uint32_t word_be(uint64_t wi) const
+    __device__ __forceinline__ uint4 load_chunk(uint64_t ci) const
     {
-        const uint64_t byte = wi << 2;
-        if (byte + 4 <= avail) return bswap32(reinterpret_cast<const uint32_t *>(in)[wi]);
-        uint32_t v = 0;
+        const uint64_t byte = ci << 4;
+        if (vec && byte + 16 <= avail) return ld_stream_u4(in + byte);
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (byte < avail) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (byte + j < avail) v |= (uint32_t)in[byte + j] << (24 - 8 * j);
+            for (int j = 0; j < 16; j++) {
+                if (byte + j < avail) w[j >> 2] |= (uint32_t)in[byte + j] << (8 * (j & 3));
+            }
         }
-        return v;
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ __forceinline__ uint32_t next_word_be()
+    {
+        const uint32_t w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
+        if (++k == 4) {
+            k = 0;
+            cur = nxt;
+            chunk++;
+            nxt = load_chunk(chunk + 1);
+        }
+        return bswap32(w);
     }
     __device__ __forceinline__ void seek(uint32_t pos)
     {
         const uint64_t g = base_bit + pos;
         const uint64_t wi = g >> 5;
         const int sh = (int)(g & 31);
-        buf = (((uint64_t)word_be(wi) << 32) | word_be(wi + 1)) << sh;
+        chunk = wi >> 2;
+        k = (int)(wi & 3);
+        cur = load_chunk(chunk);
+        nxt = load_chunk(chunk + 1);
+        const uint64_t hi = next_word_be();
+        const uint64_t lo = next_word_be();
+        buf = ((hi << 32) | lo) << sh;
         have = 64 - sh;
-        next_word = wi + 2;
     }
     __device__ __forceinline__ uint32_t peek(int bits) const { return (uint32_t)(buf >> (64 - bits)); }
     __device__ __forceinline__ void skip(int bits)
@@ -337,7 +388,7 @@ struct BitReader {
         buf <<= bits;
         have -= bits;
         if (have <= 32) {
-            buf |= (uint64_t)word_be(next_word++) << (32 - have);
+            buf |= (uint64_t)next_word_be() << (32 - have);
             have += 32;
         }
     }
@@ -345,8 +396,8 @@ struct BitReader {
 
 // One decode step at payload bit position `pos`.  Returns the symbol (>= 0) and advances, or
 // -1 when the walk dies: then `pos` advances by one bit (any deterministic rule works for a
-// speculative start; for a true start the caller records the error) and *dead_at is the bit
-// position whose consumption walks into the absent child.
+// speculative start; on a proven start the caller records the error) and *dead_at is the bit
+// whose consumption walks into the absent child.
 __device__ __forceinline__ int decode_one(const DecSmem &sm, BitReader &br, uint32_t &pos,
                                           uint32_t *dead_at)
 {
@@ -373,8 +424,7 @@ __device__ __forceinline__ int decode_one(const DecSmem &sm, BitReader &br, uint
         const int nx = bit ? sm.rch[node] : sm.lch[node];
         if (nx < 0) {
             *dead_at = pos;
-            // rewind rule: speculative restart one bit after where this walk began
-            pos = p0 + 1;
+            pos = p0 + 1;  // same rule as a table miss: resume one bit after the failed start
             br.seek(pos);
             return -1;
         }
@@ -385,33 +435,37 @@ __device__ __forceinline__ int decode_one(const DecSmem &sm, BitReader &br, uint
     }
 }
 
-// Decode from `start` until the position reaches `limit` (a sub-block boundary) or `max_syms`
-// symbols were produced.  Returns the symbol count; *end = position after the last step;
-// *first_dead = earliest dead bit seen (0xffffffff if none) with the symbol index before it.
-template <bool WRITE>
-__device__ __forceinline__ uint32_t decode_span(const DecSmem &sm, BitReader &br, uint32_t start,
-                                                uint32_t limit, uint32_t max_syms, uint8_t *dst,
-                                                uint32_t *end, uint32_t *first_dead,
-                                                uint32_t *syms_before_dead)
+// Count symbols from `pos` (reader already positioned there) until the position reaches
+// `limit` or `max_syms` symbols were seen.  Returns the count, *end = final position.
+__device__ __forceinline__ uint32_t count_span(const DecSmem &sm, BitReader &br, uint32_t pos,
+                                               uint32_t limit, uint32_t max_syms, uint32_t *end)
 {
-    uint32_t pos = start, n = 0;
-    uint32_t dead = 0xffffffffu, dead_n = 0;
-    br.seek(pos);
-    while (pos < limit && n < max_syms) {
+    uint32_t n = 0, d;
+    while (pos < limit && n < max_syms) n += decode_one(sm, br, pos, &d) >= 0;
+    *end = pos;
+    return n;
+}
+
+// Decode exactly `need` symbols from `pos` into dst (or nowhere when dst == nullptr).
+// Returns the end position; *dead = first dead bit met on the way (0xffffffff if none).
+__device__ __forceinline__ uint32_t emit_span(const DecSmem &sm, BitReader &br, uint32_t pos,
+                                              uint32_t limit, uint32_t need, uint8_t *dst,
+                                              uint32_t *produced, uint32_t *dead)
+{
+    uint32_t n = 0, first_dead = 0xffffffffu;
+    while (n < need && pos < limit) {
         uint32_t d = 0;
-        const int s = decode_one(sm, br, pos, &d);
-        if (s >= 0) {
-            if (WRITE) dst[n] = (uint8_t)s;
+        const int sy = decode_one(sm, br, pos, &d);
+        if (sy >= 0) {
+            if (dst) dst[n] = (uint8_t)sy;
             n++;
-        } else if (dead == 0xffffffffu) {
-            dead = d;
-            dead_n = n;
+        } else if (first_dead == 0xffffffffu) {
+            first_dead = d;
         }
     }
-    *end = pos;
-    *first_dead = dead;
-    *syms_before_dead = dead_n;
-    return n;
+    *produced = n;
+    *dead = first_dead;
+    return pos;
 }
 
 __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
@@ -659,32 +713,53 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         br.in = a.in;
         br.avail = a.avail;
         br.base_bit = pay0 << 3;
+        br.vec = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
         const uint32_t max_syms = doomed ? 0xffffffffu : (uint32_t)orig_len;
 
-        // phase 1: speculative decode of every sub-block from its nominal start
-        uint32_t start = my_lo, end = my_lo, cnt = 0, dead = 0xffffffffu, dead_n = 0;
-        if (my_lo < my_hi)
-            cnt = decode_span<false>(sm, br, start, my_hi, max_syms, nullptr, &end, &dead, &dead_n);
+        // phase 1: speculative count of every sub-block from its nominal start
+        uint32_t start = my_lo, end = my_lo, cnt = 0;
+        if (my_lo < my_hi) {
+            br.seek(start);
+            cnt = count_span(sm, br, start, my_hi, max_syms, &end);
+        }
         sm.sub_end[tid] = end;
         __syncthreads();
 
-        // phase 2: sync-point fix-up.  Thread t's true start is where thread t-1 ended;
-        // re-decode while that belief changes.  Thread t is final after at most t rounds;
-        // Huffman codes re-synchronise quickly, so in practice after two.
+        // phase 2: sync-point fix-up.  Thread t's true start is where thread t-1 ended.  When
+        // that differs from the start it used, it walks the new and the old trajectory in
+        // lockstep only until they meet (Huffman codes re-synchronise within a few symbols);
+        // from there on the old count and end stay valid.  Thread t is final after at most t
+        // rounds, in practice after two.
         for (int round = 0; round < kDecThreads; round++) {
             const uint32_t want = tid == 0 ? 0u : sm.sub_end[tid - 1];
             const bool redo = tid > 0 && want != start;
             __syncthreads();
             if (redo) {
-                start = want;
-                if (start < my_hi) {
-                    cnt = decode_span<false>(sm, br, start, my_hi, max_syms, nullptr, &end, &dead,
-                                             &dead_n);
-                } else {
+                if (want >= my_hi) {
+                    start = want;
                     cnt = 0;
-                    end = start;
-                    dead = 0xffffffffu;
-                    dead_n = 0;
+                    end = want;
+                } else {
+                    BitReader old = br;
+                    uint32_t pa = want, pb = start, ca = 0, cb = 0, d;
+                    br.seek(pa);
+                    const bool has_old = start < my_hi;
+                    if (has_old) old.seek(pb);
+                    // advance whichever trajectory is behind until both stand on the same bit
+                    while (pa < my_hi && ca < max_syms && !(has_old && pa == pb)) {
+                        if (!has_old || pa < pb || pb >= my_hi) {
+                            ca += decode_one(sm, br, pa, &d) >= 0;
+                        } else {
+                            cb += decode_one(sm, old, pb, &d) >= 0;
+                        }
+                    }
+                    if (has_old && pa == pb && pa < my_hi && ca < max_syms) {
+                        cnt = ca + (cnt - cb);  // merged: the rest of the old walk is reused
+                    } else {
+                        cnt = ca;               // ran to the boundary on its own
+                        end = pa;
+                    }
+                    start = want;
                 }
                 sm.sub_end[tid] = end;
             }
@@ -704,44 +779,41 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         const uint64_t before = (uint64_t)sm.warp_tot[tid >> 5] + incl - cnt;  // symbols before mine
         if (tid == kDecThreads - 1) sm.total_syms = before + cnt;
 
-        // true-chain errors: a dead walk before all needed symbols were produced
-        if (dead != 0xffffffffu && before + dead_n < orig_len) atomicMin(&sm.err_pos, dead);
-
-        uint32_t need = 0;
-        if (before < orig_len) need = (uint32_t)min((uint64_t)cnt, orig_len - before);
-        const bool finisher = need > 0 && before + need == orig_len;
         const uint64_t out0 = a.out_off[j];
         const bool can_write = !a.count_only && !doomed && out0 + orig_len <= a.out_cap;
         const bool use_stage = can_write && orig_len <= a.stage_cap;
 
-        if (need > 0 && (finisher || can_write)) {
-            uint8_t *dst = use_stage ? stage + before : a.out + out0 + before;
-            uint32_t e2, d2, dn2;
-            if (can_write)
-                decode_span<true>(sm, br, start, 0xffffffffu, need, dst, &e2, &d2, &dn2);
-            else
-                decode_span<false>(sm, br, start, 0xffffffffu, need, nullptr, &e2, &d2, &dn2);
+        // phase 4: every start is proven now: decode for real.  A dead walk met on the way is
+        // an error of the stream, not of the speculation, so sub-blocks in front of the
+        // block's last symbol are walked to their very end even if they hold no symbol.
+        if (before < orig_len && start < end) {
+            const bool finisher = before + cnt >= orig_len;  // the block completes in here
+            const uint32_t need = finisher ? (uint32_t)(orig_len - before) : 0xffffffffu;
+            const uint32_t limit = finisher ? 0xffffffffu : end;
+            uint8_t *dst = !can_write ? nullptr : use_stage ? stage + before : a.out + out0 + before;
+            uint32_t got, dead;
+            br.seek(start);
+            const uint32_t e2 = emit_span(sm, br, start, limit, need, dst, &got, &dead);
+            if (dead != 0xffffffffu) atomicMin(&sm.err_pos, dead);
             if (finisher) sm.end_bit = e2;
         }
         __syncthreads();
 
         // The guessed extent was short (the next candidate was a false positive inside this
-        // payload): the chain runs past the last sub-block, whose end is proven by now, and one
-        // thread finishes serially.  Rare by construction of the signature.
+        // payload) or the block cannot complete: the chain runs past the last sub-block, whose
+        // end is proven by now, and one thread walks on serially.  Rare by construction.
         if (tid == 0 && sm.total_syms < orig_len) {
             const uint32_t from = sm.sub_end[kDecThreads - 1];
             const uint64_t have = sm.total_syms;
             const uint64_t rest = orig_len - have;
-            uint32_t e2 = from, d2 = 0xffffffffu, dn2 = 0, got = 0;
+            uint32_t e2 = from, dead = 0xffffffffu, got = 0;
             if (from < room_bits) {
                 const uint32_t lim_syms = rest > 0xffffffffull ? 0xffffffffu : (uint32_t)rest;
-                uint8_t *dst = use_stage ? stage + have : a.out + out0 + have;
-                if (can_write)
-                    got = decode_span<true>(sm, br, from, room_bits, lim_syms, dst, &e2, &d2, &dn2);
-                else
-                    got = decode_span<false>(sm, br, from, room_bits, lim_syms, nullptr, &e2, &d2, &dn2);
+                uint8_t *dst = !can_write ? nullptr : use_stage ? stage + have : a.out + out0 + have;
+                br.seek(from);
+                e2 = emit_span(sm, br, from, room_bits, lim_syms, dst, &got, &dead);
             }
-            if (d2 != 0xffffffffu) atomicMin(&sm.err_pos, d2);
+            if (dead != 0xffffffffu) atomicMin(&sm.err_pos, dead);
             if (got == rest) {
                 sm.end_bit = e2;
             } else {

@@ -87,18 +87,24 @@ __device__ __forceinline__ void hist_u4(uint32_t *h, const uint4 &v)
     hist_word(h, v.w);
 }
 
+// Four counter sets per warp (lane & 3 picks one) cut same-symbol serialisation of the shared
+// memory atomics on skewed data; the sets are skewed by 8 banks so that one symbol counted in
+// two sets does not collide on a bank either.
+constexpr int kHistSets = 4;
+constexpr int kHistStride = 256 + 8;
+
 __global__ void __launch_bounds__(kEncWarps * 32) k_seg_hist(EncArgs a)
 {
-    __shared__ uint32_t sh[kEncWarps][256];
+    __shared__ uint32_t sh[kEncWarps][kHistSets * kHistStride];
     const int lane = lane_id();
     const int w = warp_in_cta();
     const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
     if (g >= a.npass * a.nspb) return;
 
-    uint32_t *h = sh[w];
-#pragma unroll
-    for (int i = 0; i < 8; i++) h[lane + 32 * i] = 0;
+    uint32_t *hw = sh[w];
+    for (int i = lane; i < kHistSets * kHistStride; i += 32) hw[i] = 0;
     __syncwarp();
+    uint32_t *h = hw + (lane & (kHistSets - 1)) * kHistStride;
 
     const uint64_t b = a.blk0 + g / a.nspb;
     const uint32_t k = (uint32_t)(g % a.nspb);
@@ -133,7 +139,11 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_seg_hist(EncArgs a)
     // lane l owns bins 8l .. 8l+7 -> one 16-byte store per lane, 512 contiguous bytes per warp
     uint32_t c[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) c[i] = h[lane * 8 + i];
+    for (int i = 0; i < 8; i++) {
+        c[i] = 0;
+#pragma unroll
+        for (int q = 0; q < kHistSets; q++) c[i] += hw[q * kHistStride + lane * 8 + i];
+    }
     uint4 o;
     o.x = c[0] | (c[1] << 16);
     o.y = c[2] | (c[3] << 16);
@@ -154,6 +164,7 @@ struct BuildSmem {
     uint16_t lch[256];   // children of merge node 256 + j
     uint16_t rch[256];
     uint16_t par[512];   // parent of every node
+    uint16_t rend[256];  // for the first merge node of an equal-weight run: one past its last
     uint8_t len[256];    // code length per symbol (0 = absent)
 };
 
@@ -220,64 +231,78 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build(EncArgs a)
         }
     }
 
-    // (3) two-queue merge, serial in lane 0.  Leaves are consumed in key order from sm.key;
-    // merge nodes are created with non-decreasing weight, so the live ones are
-    // [head, top) (the front run of equal weight, consumed newest first) plus [nxt, made).
+    // (3) two-queue merge, serial in lane 0 with all queue state in registers.  Leaves are
+    // consumed in key order from sm.key (two keys prefetched).  Merge nodes are created with
+    // non-decreasing weight, so they form runs of equal weight in creation order; the live
+    // ones are [head, top) -- the front run, consumed newest first, its weight in `runw` --
+    // plus [nxt, made).  Run extents are recorded when nodes are created (sm.rend), so no
+    // scanning is needed when a run is opened.
     if (lane == 0) {
-        uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0;
+        uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0, run_first = 0;
+        W runw = 0, last_w = 0;
+        W k0 = sm.key[0];                 // n >= 1
+        W k1 = n > 1 ? sm.key[1] : kMax;
         for (;;) {
-            uint32_t pick[2];
-            W pw[2];
+            uint32_t pick0 = 0, pick1 = kNone16;
+            W w0 = 0, w1 = 0;
             int got = 0;
-#pragma unroll 1
+#pragma unroll
             for (int s = 0; s < 2; s++) {
-                if (top == head) {  // front run used up: open the next one
-                    head = top = nxt;
-                    if (head < made) {
-                        const W rw = sm.iw[head];
-                        uint32_t e = head + 1;
-                        while (e < made && sm.iw[e] == rw) e++;
-                        nxt = top = e;
-                    }
-                } else if (top == nxt) {  // untouched run may have grown at its end
-                    const W rw = sm.iw[head];
-                    while (nxt < made && sm.iw[nxt] == rw) nxt++;
-                    top = nxt;
+                if (top == head && nxt < made) {  // front run used up: open the next one
+                    head = nxt;
+                    runw = sm.iw[nxt];
+                    top = nxt = sm.rend[nxt];
                 }
                 const bool has_i = top > head;
-                const bool has_l = li < n;
-                if (!has_i && !has_l) break;
-                const W ikey = has_i ? make_key<W>(sm.iw[head], 255u + top) : kMax;
-                const W lkey = has_l ? sm.key[li] : kMax;
-                if (has_i && ikey < lkey) {
+                const W ikey = has_i ? make_key<W>(runw, 255u + top) : kMax;
+                if (ikey == kMax && k0 == kMax) break;  // nothing left (second pick only)
+                uint32_t pick;
+                W pw;
+                if (ikey < k0) {
                     top--;
-                    pick[s] = 256u + top;
-                    pw[s] = sm.iw[head];
+                    pick = 256u + top;
+                    pw = runw;
+                    if (top == head) head = top = nxt;
                 } else {
+                    pick = 511u - (uint32_t)(k0 & 511u);
+                    pw = k0 >> 9;
                     li++;
-                    pick[s] = 511u - (uint32_t)(lkey & 511u);
-                    pw[s] = lkey >> 9;
+                    k0 = k1;
+                    k1 = li + 1 < n ? sm.key[li + 1] : kMax;
+                }
+                if (s == 0) {
+                    pick0 = pick;
+                    w0 = pw;
+                } else {
+                    pick1 = pick;
+                    w1 = pw;
                 }
                 got++;
             }
-            // got >= 1 here: the loop ends right after the unary root is made
             const uint32_t me = 256u + made;
-            uint32_t size = 1;
-            sm.lch[made] = (uint16_t)pick[0];
-            sm.par[pick[0]] = (uint16_t)me;
-            size += pick[0] < 256u ? 3u : sm.isz[pick[0] - 256u];
-            W weight = pw[0];
+            uint32_t size = 1 + (pick0 < 256u ? 3u : sm.isz[pick0 - 256u]);
+            sm.lch[made] = (uint16_t)pick0;
+            sm.par[pick0] = (uint16_t)me;
+            W weight = w0;
             if (got == 2) {
-                sm.rch[made] = (uint16_t)pick[1];
-                sm.par[pick[1]] = (uint16_t)me;
-                size += pick[1] < 256u ? 3u : sm.isz[pick[1] - 256u];
-                weight += pw[1];
+                sm.par[pick1] = (uint16_t)me;
+                size += pick1 < 256u ? 3u : sm.isz[pick1 - 256u];
+                weight += w1;
             } else {
-                sm.rch[made] = (uint16_t)kNone16;
                 size += 1;  // the absent right child of the unary root
             }
+            sm.rch[made] = (uint16_t)pick1;
             sm.iw[made] = weight;
             sm.isz[made] = (uint16_t)size;
+            // run bookkeeping: extend the newest run or start a new one
+            if (made == 0 || weight != last_w) run_first = made;
+            sm.rend[run_first] = (uint16_t)(made + 1);
+            last_w = weight;
+            // an open front run that is still untouched and is the newest run grows with it
+            if (top > head && top == nxt && nxt == made && weight == runw) {
+                top++;
+                nxt++;
+            }
             made++;
             if (got < 2) break;
         }
@@ -458,10 +483,11 @@ __device__ __forceinline__ void store_word(const OutRange &r, uint64_t widx, uin
 }
 
 // Insert the top `l` bits of `t` (left aligned, other bits zero) at bit `nb` of the hi:lo
-// window; flush a finished 32-bit word into the staging buffer.
+// window; a finished 32-bit word goes to the staging buffer with a plain store (every word
+// is finished by exactly one lane; the bits earlier lanes left in a lane's first word are
+// OR-ed in afterwards, see pack_flush_carry).  The body is small enough to be predicated.
 struct BitAcc {
     uint32_t hi, lo, nb, widx;
-    bool first;
 };
 
 __device__ __forceinline__ void acc_put(BitAcc &s, uint32_t *stage, uint32_t t, uint32_t l)
@@ -470,17 +496,43 @@ __device__ __forceinline__ void acc_put(BitAcc &s, uint32_t *stage, uint32_t t, 
     s.lo |= __funnelshift_r(0u, t, s.nb);
     s.nb += l;
     if (s.nb >= 32) {
-        if (s.first) {
-            atomicOr(&stage[s.widx], s.hi);  // word shared with the previous lane
-            s.first = false;
-        } else {
-            stage[s.widx] = s.hi;
-        }
+        stage[s.widx] = s.hi;
         s.hi = s.lo;
         s.lo = 0;
         s.nb -= 32;
         s.widx++;
     }
+}
+
+// After every lane ran its symbols through acc_put: hand the unfinished tail of each lane
+// to the lane that finishes that word.  A segmented OR-scan over the lanes (segments start
+// at lanes that finished at least one word) yields, for every lane, the bits its
+// predecessors left in its first word; `carry` is the same thing across iterations.
+// Returns the warp's new carry (the unfinished word after lane 31).
+__device__ __forceinline__ uint32_t pack_flush_carry(const BitAcc &acc, uint32_t first_widx,
+                                                    uint32_t *stage, uint32_t carry)
+{
+    const int lane = lane_id();
+    const bool done_one = acc.widx != first_widx;   // this lane finished >= 1 word
+    const uint32_t heads = __ballot_sync(kFull, done_one);
+    uint32_t v = acc.hi;  // own unfinished bits (zero when nb == 0)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t pv = __shfl_up_sync(kFull, v, d);
+        // take the predecessor's run only if no segment starts in lanes (lane-d, lane]
+        if (lane >= d && ((heads >> (lane - d + 1)) & ((1u << d) - 1u)) == 0) v |= pv;
+    }
+    uint32_t in = __shfl_up_sync(kFull, v, 1);
+    const uint32_t below = heads & ((1u << lane) - 1u);  // segment starts among earlier lanes
+    if (lane == 0) in = 0;
+    if (below == 0) in |= carry;
+    if (done_one) {
+        if (in) stage[first_widx] |= in;  // own word: written by this lane above
+    }
+    // lanes that finished nothing pass (in | own bits) on: that is what the scan computed
+    uint32_t out = __shfl_sync(kFull, v, 31);
+    if (heads == 0) out |= carry;
+    return out;
 }
 
 __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
@@ -620,26 +672,19 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
             const uint32_t incl = warp_incl_scan(total_l);
             const uint32_t total = __shfl_sync(kFull, incl, 31);
             const uint32_t start = q + incl - total_l;
-            const uint32_t nwords = (q + total + 31) >> 5;
-
-            // ---- staging window: word 0 carries the unfinished word of the previous step
-            for (uint32_t i = lane; i < nwords + 1; i += 32) stage[i] = i ? 0u : carry;
-            __syncwarp();
-
             acc.hi = acc.lo = 0;
             acc.nb = start & 31;
             acc.widx = start >> 5;
-            acc.first = true;
+            const uint32_t first_widx = acc.widx;
 #pragma unroll
             for (int j = 0; j < 16; j++) acc_put(acc, stage, e[j] & ~31u, e[j] & 31u);
-            if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
+            carry = pack_flush_carry(acc, first_widx, stage, carry);
             __syncwarp();
 
             // ---- copy finished words out, coalesced
             const uint32_t nfull = (q + total) >> 5;
             for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
             q = (q + total) & 31;
-            carry = q ? stage[nfull] : 0u;
             wbase += nfull;
             __syncwarp();
         } else {
@@ -653,14 +698,10 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
             const uint32_t incl = warp_incl_scan(total_l);
             const uint32_t total = __shfl_sync(kFull, incl, 31);
             const uint32_t start = q + incl - total_l;
-            const uint32_t nwords = (q + total + 31) >> 5;
-            for (uint32_t i = lane; i < nwords + 1; i += 32) stage[i] = i ? 0u : carry;
-            __syncwarp();
-
             acc.hi = acc.lo = 0;
             acc.nb = start & 31;
             acc.widx = start >> 5;
-            acc.first = true;
+            const uint32_t first_widx = acc.widx;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const uint32_t l = (uint32_t)(e[j] & 0xffu);
@@ -669,13 +710,12 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
                 acc_put(acc, stage, (uint32_t)(t >> 32), l1);
                 acc_put(acc, stage, (uint32_t)t, l - l1);
             }
-            if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
+            carry = pack_flush_carry(acc, first_widx, stage, carry);
             __syncwarp();
 
             const uint32_t nfull = (q + total) >> 5;
             for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
             q = (q + total) & 31;
-            carry = q ? stage[nfull] : 0u;
             wbase += nfull;
             __syncwarp();
         }

@@ -83,8 +83,8 @@ struct huf_b200_ctx {
     cudaStream_t cur = nullptr;
     Arena enc_ws, dec_ws;
     uint32_t *d_status = nullptr;   // [4]
-    uint64_t *d_result = nullptr;   // [8]
-    uint64_t *h_result = nullptr;   // pinned mirror, [16]
+    uint64_t *d_result = nullptr;   // [16]
+    uint64_t *h_result = nullptr;   // pinned mirror, [32]
     uint64_t launches = 0;
     int accept_1025 = 0;
 
@@ -106,6 +106,7 @@ struct huf_b200_ctx {
     // decode call in flight
     bool dec_pending = false;
     DecArgs dec{};
+    bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
     uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode
     uint64_t dec_stage_want = 65536;
 };
@@ -186,8 +187,8 @@ huf_error_t huf_b200_ctx_create(huf_b200_ctx_t **out, int device)
     c->accept_1025 = env && env[0] == '1';
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_status, 4 * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_result, 8 * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMallocHost(&c->h_result, 16 * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_result, 16 * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_result, 32 * sizeof(uint64_t));
     if (e != cudaSuccess) {
         huf_b200_ctx_destroy(&c);
         return cuda_fail(e);
@@ -408,11 +409,13 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
 
     size_t need = 0;
     need += Arena::padded(a.nchunks * sizeof(uint32_t));
+    need += Arena::padded(a.nchunks * kFindSlots * sizeof(uint32_t));
     need += Arena::padded((a.nchunks + 1) * sizeof(uint64_t));
     need += 4 * Arena::padded((max_cand + 1) * sizeof(uint64_t));
     need += Arena::padded(max_cand * sizeof(uint32_t));
     if (!c->dec_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
     a.chunk_cnt = c->dec_ws.take<uint32_t>(a.nchunks);
+    a.slots = c->dec_ws.take<uint32_t>(a.nchunks * kFindSlots);
     a.chunk_off = c->dec_ws.take<uint64_t>(a.nchunks + 1);
     a.cand = c->dec_ws.take<uint64_t>(max_cand + 1);
     a.olen = c->dec_ws.take<uint64_t>(max_cand + 1);
@@ -421,11 +424,17 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     a.blk_status = c->dec_ws.take<uint32_t>(max_cand);
     a.result = c->d_result;
 
-    CU_TRY(cudaMemsetAsync(c->d_result, 0, 8 * sizeof(uint64_t), st));
+    CU_TRY(cudaMemsetAsync(c->d_result, 0, 16 * sizeof(uint64_t), st));
     const unsigned find_grid = (unsigned)((a.nchunks + kFindWarps - 1) / kFindWarps);
-    CTX_LAUNCH(c, k_find<false>, find_grid, kFindWarps * 32, 0, st, a);
-    CTX_LAUNCH(c, k_scan_chunks, 1, kScanThreads, 0, st, a);
-    CTX_LAUNCH(c, k_find<true>, find_grid, kFindWarps * 32, 0, st, a);
+    if (c->dec_dense) {
+        CTX_LAUNCH(c, k_find<0>, find_grid, kFindWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_scan_chunks, 1, kScanThreads, 0, st, a);
+        CTX_LAUNCH(c, k_find<1>, find_grid, kFindWarps * 32, 0, st, a);
+    } else {
+        CTX_LAUNCH(c, k_find<2>, find_grid, kFindWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_scan_chunks, 1, kScanThreads, 0, st, a);
+        CTX_LAUNCH(c, k_compact, (unsigned)((a.nchunks + 255) / 256), 256, 0, st, a);
+    }
     CTX_LAUNCH(c, k_gather, c->sm_count * 4, 256, 0, st, a);
     CTX_LAUNCH(c, k_scan_olen, 1, kScanThreads, 0, st, a);
     if (!plan_only) {
@@ -451,7 +460,7 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         CTX_LAUNCH(c, k_verify, 1, kScanThreads, 0, st, a);
     }
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_result, 8 * sizeof(uint64_t),
+    CU_TRY(cudaMemcpyAsync(c->h_result, c->d_result, 16 * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, st));
     if (plan_only) {
         // total decoded size of the candidate chain = out_off[ncand]; fetched after the sync
@@ -472,6 +481,7 @@ huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     c->cur = pick_stream(c, stream);
     c->launches = 0;
     c->ntimed = 0;
+    c->dec_dense = false;
     c->dec_pending = true;
     DecArgs &a = c->dec;
     memset(&a, 0, sizeof(a));
@@ -497,6 +507,14 @@ huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_
     for (;;) {
         CU_TRY(cudaStreamSynchronize(c->cur));
         const uint64_t *r = c->h_result;
+        if (r[8] && !c->dec_dense) {
+            // more headers per chunk than the sparse single-pass scan parks: this stream has
+            // tiny blocks; rerun (and keep running) with the exact two-pass scan
+            c->dec_dense = true;
+            huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, 0);
+            if (e != HUF_ERROR_SUCCESS) return e;
+            continue;
+        }
         if (r[6] > c->dec.max_cand) {
             // candidate workspace too small for this stream: rerun the pass with the exact size
             huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, r[6] + 16);
@@ -527,6 +545,7 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
     *out_len = 0;
     if (nblocks) *nblocks = 0;
     if (!length) return HUF_ERROR_SUCCESS;
+    c->dec_dense = false;
     DecArgs &a = c->dec;
     memset(&a, 0, sizeof(a));
     a.in = static_cast<const uint8_t *>(d_in);
@@ -537,6 +556,10 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
         huf_error_t e = dec_enqueue(c, 0, 0, true, hint);
         if (e != HUF_ERROR_SUCCESS) return e;
         CU_TRY(cudaStreamSynchronize(c->cur));
+        if (c->h_result[8] && !c->dec_dense) {
+            c->dec_dense = true;
+            continue;
+        }
         if (c->h_result[6] > a.max_cand) {
             hint = c->h_result[6] + 16;
             continue;

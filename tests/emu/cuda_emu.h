@@ -260,6 +260,14 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d)
     const unsigned l = hufemu::lane();
     return hufemu::warp_exchange(v, [&](uint64_t *x) { return l >= d ? hufemu::from_bits<T>(x[l - d]) : v; });
 }
+inline uint32_t __ballot_sync(unsigned, int pred)
+{
+    return hufemu::warp_exchange((uint32_t)(pred != 0), [&](uint64_t *x) {
+        uint32_t m = 0;
+        for (int l = 0; l < 32; l++) m |= (uint32_t)(x[l] & 1) << l;
+        return m;
+    });
+}
 template <typename T>
 inline T __shfl_down_sync(unsigned, T v, unsigned d)
 {
