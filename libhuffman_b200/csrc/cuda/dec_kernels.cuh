@@ -24,7 +24,7 @@ namespace hufb200 {
 
 constexpr int kFindWarps = 8;
 constexpr uint32_t kFindChunk = 32768;  // bytes scanned per warp
-constexpr int kDecThreads = 256;
+constexpr int kDecThreads = 512;
 constexpr int kLutBits = 12;
 constexpr int kLutSize = 1 << kLutBits;
 constexpr int kMaxNodes = 1026;
@@ -61,6 +61,7 @@ struct DecArgs {
                            // [5] chain complete flag [6] candidates found (may exceed max_cand)
                            // [7] largest orig_len among the candidates
                            // [8] sparse-mode slot overflow (rerun with the two-pass scan)
+                           // [9] largest block extent (header + payload bytes) seen
 };
 
 // ------------------------------------------------------------------------------------------
@@ -261,6 +262,11 @@ __global__ void k_gather(DecArgs a)
         if (ol > 8ull * room) ol = 0;
         a.olen[j] = ol;
         if (ol) atomicMax(reinterpret_cast<unsigned long long *>(&a.result[7]), (unsigned long long)ol);
+        // extent of this block's header + payload as the candidate list sees it: sizes the
+        // shared-memory payload staging of k_decode on the next call
+        const uint64_t next = j + 1 < n ? a.cand[j + 1] : a.avail;
+        if (next > off)
+            atomicMax(reinterpret_cast<unsigned long long *>(&a.result[9]), (unsigned long long)(next - off));
     }
 }
 
@@ -330,67 +336,36 @@ struct Terminal {
     uint16_t pad;
 };
 
-// MSB-first bit window over the payload, addressed in payload-relative bit positions.
-// The stream is fetched in 16-byte chunks with one chunk prefetched ahead, so that the global
-// load latency is off the per-symbol dependency chain; bytes past `avail` read as zero.
-struct BitReader {
-    const uint8_t *in;
-    uint64_t avail;      // readable bytes of the whole stream
-    uint64_t base_bit;   // global bit position of payload bit 0
-    uint64_t buf;        // next bits, left aligned
-    int have;            // valid bits in buf
-    uint4 cur, nxt;      // chunk being consumed and the prefetched one
-    uint64_t chunk;      // index of `cur`
-    int k;               // next 32-bit word of `cur` to append
-    bool vec;            // stream base is 16-byte aligned
+// Stateless MSB-first bit access to one block's payload, addressed by payload-relative bit
+// position.  SMEM = true: the payload was staged into shared memory as big-endian 32-bit
+// words (bit 0 of word 0 is `bias` bits in front of payload bit 0), so a 32-bit window costs
+// two LDS and one funnel shift and carries no per-thread state: every lane of a warp runs
+// the same instructions.  SMEM = false reads the bytes from global memory, bounds checked
+// (used when the payload does not fit and for the serial tail walk).
+template <bool SMEM>
+struct Bits {
+    const uint32_t *sw;   // staged words
+    uint32_t bias;        // bits between staged bit 0 and payload bit 0
+    uint32_t last_word;   // highest index that may be read (words beyond read as the last one)
+    const uint8_t *in;    // whole stream (global)
+    uint64_t avail;
+    uint64_t pay0;
 
-    __device__ __forceinline__ uint4 load_chunk(uint64_t ci) const
+    __device__ __forceinline__ uint32_t window(uint32_t pos) const
     {
-        const uint64_t byte = ci << 4;
-        if (vec && byte + 16 <= avail) return ld_stream_u4(in + byte);
-        uint32_t w[4] = {0, 0, 0, 0};
-        if (byte < avail) {
+        if (SMEM) {
+            const uint32_t p = pos + bias;
+            const uint32_t i = min(p >> 5, last_word);
+            return __funnelshift_l(sw[i + 1], sw[i], p & 31);
+        }
+        const uint64_t byte = pay0 + (pos >> 3);
+        uint64_t v = 0;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (byte + j < avail) w[j >> 2] |= (uint32_t)in[byte + j] << (8 * (j & 3));
-            }
+        for (int q = 0; q < 5; q++) {
+            const uint64_t at = byte + q;
+            v = (v << 8) | (at < avail ? in[at] : 0u);
         }
-        return make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    __device__ __forceinline__ uint32_t next_word_be()
-    {
-        const uint32_t w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
-        if (++k == 4) {
-            k = 0;
-            cur = nxt;
-            chunk++;
-            nxt = load_chunk(chunk + 1);
-        }
-        return bswap32(w);
-    }
-    __device__ __forceinline__ void seek(uint32_t pos)
-    {
-        const uint64_t g = base_bit + pos;
-        const uint64_t wi = g >> 5;
-        const int sh = (int)(g & 31);
-        chunk = wi >> 2;
-        k = (int)(wi & 3);
-        cur = load_chunk(chunk);
-        nxt = load_chunk(chunk + 1);
-        const uint64_t hi = next_word_be();
-        const uint64_t lo = next_word_be();
-        buf = ((hi << 32) | lo) << sh;
-        have = 64 - sh;
-    }
-    __device__ __forceinline__ uint32_t peek(int bits) const { return (uint32_t)(buf >> (64 - bits)); }
-    __device__ __forceinline__ void skip(int bits)
-    {
-        buf <<= bits;
-        have -= bits;
-        if (have <= 32) {
-            buf |= (uint64_t)next_word_be() << (32 - have);
-            have += 32;
-        }
+        return (uint32_t)(v >> (8 - (pos & 7)));
     }
 };
 
@@ -398,74 +373,185 @@ struct BitReader {
 // -1 when the walk dies: then `pos` advances by one bit (any deterministic rule works for a
 // speculative start; on a proven start the caller records the error) and *dead_at is the bit
 // whose consumption walks into the absent child.
-__device__ __forceinline__ int decode_one(const DecSmem &sm, BitReader &br, uint32_t &pos,
+template <bool SMEM>
+__device__ __forceinline__ int decode_one(const DecSmem &sm, const Bits<SMEM> &bits, uint32_t &pos,
                                           uint32_t *dead_at)
 {
-    const uint16_t e = sm.lut[br.peek(kLutBits)];
+    const uint16_t e = sm.lut[bits.window(pos) >> (32 - kLutBits)];
     if (!(e & (kLutLong | kLutDead))) {
-        const int len = e >> 8;
-        br.skip(len);
-        pos += len;
+        pos += e >> 8;
         return e & 0xff;
     }
     if (e & kLutDead) {
         *dead_at = pos + (e & 0xf) - 1;
-        br.skip(1);
         pos += 1;
         return -1;
     }
     // long code: continue bit by bit from the node reached after kLutBits bits
     int node = e & 0x7ff;
-    const uint32_t p0 = pos;
-    br.skip(kLutBits);
-    pos += kLutBits;
+    uint32_t p = pos + kLutBits;
     for (;;) {
-        const int bit = br.peek(1);
+        const int bit = bits.window(p) >> 31;
         const int nx = bit ? sm.rch[node] : sm.lch[node];
         if (nx < 0) {
-            *dead_at = pos;
-            pos = p0 + 1;  // same rule as a table miss: resume one bit after the failed start
-            br.seek(pos);
+            *dead_at = p;
+            pos += 1;  // same rule as a table miss: resume one bit after the failed start
             return -1;
         }
-        br.skip(1);
-        pos += 1;
+        p++;
         node = nx;
-        if (sm.lch[node] < 0 && sm.rch[node] < 0) return (uint8_t)sm.elems[node];
+        if (sm.lch[node] < 0 && sm.rch[node] < 0) {
+            pos = p;
+            return (uint8_t)sm.elems[node];
+        }
     }
 }
 
-// Count symbols from `pos` (reader already positioned there) until the position reaches
-// `limit` or `max_syms` symbols were seen.  Returns the count, *end = final position.
-__device__ __forceinline__ uint32_t count_span(const DecSmem &sm, BitReader &br, uint32_t pos,
-                                               uint32_t limit, uint32_t max_syms, uint32_t *end)
+// Count symbols from `pos` until the position reaches `limit` or `max_syms` symbols were seen.
+template <bool SMEM>
+__device__ __forceinline__ uint32_t count_span(const DecSmem &sm, const Bits<SMEM> &bits,
+                                               uint32_t pos, uint32_t limit, uint32_t max_syms,
+                                               uint32_t *end)
 {
     uint32_t n = 0, d;
-    while (pos < limit && n < max_syms) n += decode_one(sm, br, pos, &d) >= 0;
+    while (pos < limit && n < max_syms) n += decode_one(sm, bits, pos, &d) >= 0;
     *end = pos;
     return n;
 }
 
-// Decode exactly `need` symbols from `pos` into dst (or nowhere when dst == nullptr).
-// Returns the end position; *dead = first dead bit met on the way (0xffffffff if none).
-__device__ __forceinline__ uint32_t emit_span(const DecSmem &sm, BitReader &br, uint32_t pos,
-                                              uint32_t limit, uint32_t need, uint8_t *dst,
-                                              uint32_t *produced, uint32_t *dead)
+// Decode `need` symbols from the proven position `pos` into dst (nullptr: nowhere).  Output
+// leaves in 16-byte stores once dst is aligned.  A dead walk is an error of the stream: its
+// first bit is returned in *dead (the step then counts as a symbol so that the walk stays
+// bounded; the block is reported as failed anyway).  Returns the end position.
+template <bool SMEM>
+__device__ __forceinline__ uint32_t emit_span(const DecSmem &sm, const Bits<SMEM> &bits,
+                                              uint32_t pos, uint32_t need, uint8_t *dst,
+                                              uint32_t *dead)
 {
     uint32_t n = 0, first_dead = 0xffffffffu;
-    while (n < need && pos < limit) {
+    auto one = [&]() -> uint32_t {
         uint32_t d = 0;
-        const int sy = decode_one(sm, br, pos, &d);
-        if (sy >= 0) {
-            if (dst) dst[n] = (uint8_t)sy;
+        const int sy = decode_one(sm, bits, pos, &d);
+        if (sy < 0 && first_dead == 0xffffffffu) first_dead = d;
+        return (uint32_t)sy & 0xffu;
+    };
+    if (!dst) {
+        while (n < need) {
+            one();
             n++;
-        } else if (first_dead == 0xffffffffu) {
-            first_dead = d;
         }
+    } else {
+        const uint32_t head = min(need, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+        while (n < head) dst[n++] = (uint8_t)one();
+        while (need - n >= 16) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                w[q] = one();
+                w[q] |= one() << 8;
+                w[q] |= one() << 16;
+                w[q] |= one() << 24;
+            }
+            *reinterpret_cast<uint4 *>(dst + n) = make_uint4(w[0], w[1], w[2], w[3]);
+            n += 16;
+        }
+        while (n < need) dst[n++] = (uint8_t)one();
     }
-    *produced = n;
     *dead = first_dead;
     return pos;
+}
+
+// The decode phases of one block, for either payload source.
+template <bool SMEM>
+__device__ __forceinline__ void decode_phases(DecSmem &sm, const Bits<SMEM> &bits, const DecArgs &a,
+                                              uint64_t j, uint64_t orig_len, bool doomed,
+                                              uint32_t room_bits, uint32_t sub)
+{
+    const int tid = threadIdx.x;
+    const uint32_t my_lo = (uint32_t)min((uint64_t)tid * sub, (uint64_t)room_bits);
+    const uint32_t my_hi = (uint32_t)min((uint64_t)(tid + 1) * sub, (uint64_t)room_bits);
+    const uint32_t max_syms = doomed ? 0xffffffffu : (uint32_t)orig_len;
+
+    // phase 1: speculative count of every sub-block from its nominal start
+    uint32_t start = my_lo, end = my_lo, cnt = 0;
+    if (my_lo < my_hi) cnt = count_span(sm, bits, start, my_hi, max_syms, &end);
+    sm.sub_end[tid] = end;
+    __syncthreads();
+
+    // phase 2: sync-point fix-up.  Thread t's true start is where thread t-1 ended.  When that
+    // differs from the start it used, it walks the new and the old trajectory in lockstep only
+    // until they meet (Huffman codes re-synchronise within a few symbols); from there on the
+    // old count and end stay valid.  Thread t is final after at most t rounds, in practice two.
+    for (int round = 0; round < kDecThreads; round++) {
+        const uint32_t want = tid == 0 ? 0u : sm.sub_end[tid - 1];
+        const bool redo = tid > 0 && want != start;
+        __syncthreads();
+        if (redo) {
+            if (want >= my_hi) {
+                cnt = 0;
+                end = want;
+            } else {
+                const bool has_old = start < my_hi;
+                uint32_t pa = want, pb = start, ca = 0, cb = 0, d;
+                // advance whichever trajectory is behind until both stand on the same bit
+                while (pa < my_hi && ca < max_syms && !(has_old && pa == pb)) {
+                    if (!has_old || pa < pb || pb >= my_hi) {
+                        ca += decode_one(sm, bits, pa, &d) >= 0;
+                    } else {
+                        cb += decode_one(sm, bits, pb, &d) >= 0;
+                    }
+                }
+                if (has_old && pa == pb && pa < my_hi && ca < max_syms) {
+                    cnt = ca + (cnt - cb);  // merged: the rest of the old walk is reused
+                } else {
+                    cnt = ca;               // ran to the boundary on its own
+                    end = pa;
+                }
+            }
+            start = want;
+            sm.sub_end[tid] = end;
+        }
+        if (!__syncthreads_or(redo)) break;
+    }
+
+    // phase 3: symbol-count scan -> output index of every sub-block
+    const uint32_t incl = warp_incl_scan(cnt);
+    if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        const uint32_t t = tid < kDecThreads / 32 ? sm.warp_tot[tid] : 0;
+        const uint32_t ti = warp_incl_scan(t);
+        if (tid < kDecThreads / 32) sm.warp_tot[tid] = ti - t;
+    }
+    __syncthreads();
+    const uint64_t before = (uint64_t)sm.warp_tot[tid >> 5] + incl - cnt;  // symbols before mine
+    if (tid == kDecThreads - 1) sm.total_syms = before + cnt;
+
+    const uint64_t out0 = a.out_off[j];
+    const bool can_write = !a.count_only && !doomed && out0 + orig_len <= a.out_cap;
+
+    // phase 4: every start is proven now: decode for real, straight into the output.  A dead
+    // walk met on the way is an error of the stream, not of the speculation, so sub-blocks in
+    // front of the block's last symbol are walked to their very end.
+    if (before < orig_len && start < end) {
+        const bool finisher = before + cnt >= orig_len;  // the block completes in here
+        const uint32_t need = finisher ? (uint32_t)(orig_len - before) : cnt;
+        uint8_t *dst = can_write ? a.out + out0 + before : nullptr;
+        uint32_t dead;
+        uint32_t pos = emit_span(sm, bits, start, need, dst, &dead);
+        if (finisher) {
+            sm.end_bit = pos;
+        } else {
+            uint32_t d = 0xffffffffu;
+            while (pos < end) {  // only dead bits can be left in here
+                uint32_t dd = 0;
+                if (decode_one(sm, bits, pos, &dd) < 0 && d == 0xffffffffu) d = dd;
+            }
+            if (dead == 0xffffffffu) dead = d;
+        }
+        if (dead != 0xffffffffu) atomicMin(&sm.err_pos, dead);
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
@@ -706,116 +792,86 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         uint32_t sub = (guess_bits + kDecThreads - 1) / kDecThreads;
         sub = (sub + 31u) & ~31u;
         if (sub < 64) sub = 64;
-        const uint32_t my_lo = (uint32_t)min((uint64_t)tid * sub, (uint64_t)room_bits);
-        const uint32_t my_hi = (uint32_t)min((uint64_t)(tid + 1) * sub, (uint64_t)room_bits);
 
-        BitReader br;
-        br.in = a.in;
-        br.avail = a.avail;
-        br.base_bit = pay0 << 3;
-        br.vec = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
-        const uint32_t max_syms = doomed ? 0xffffffffu : (uint32_t)orig_len;
-
-        // phase 1: speculative count of every sub-block from its nominal start
-        uint32_t start = my_lo, end = my_lo, cnt = 0;
-        if (my_lo < my_hi) {
-            br.seek(start);
-            cnt = count_span(sm, br, start, my_hi, max_syms, &end);
-        }
-        sm.sub_end[tid] = end;
-        __syncthreads();
-
-        // phase 2: sync-point fix-up.  Thread t's true start is where thread t-1 ended.  When
-        // that differs from the start it used, it walks the new and the old trajectory in
-        // lockstep only until they meet (Huffman codes re-synchronise within a few symbols);
-        // from there on the old count and end stay valid.  Thread t is final after at most t
-        // rounds, in practice after two.
-        for (int round = 0; round < kDecThreads; round++) {
-            const uint32_t want = tid == 0 ? 0u : sm.sub_end[tid - 1];
-            const bool redo = tid > 0 && want != start;
-            __syncthreads();
-            if (redo) {
-                if (want >= my_hi) {
-                    start = want;
-                    cnt = 0;
-                    end = want;
-                } else {
-                    BitReader old = br;
-                    uint32_t pa = want, pb = start, ca = 0, cb = 0, d;
-                    br.seek(pa);
-                    const bool has_old = start < my_hi;
-                    if (has_old) old.seek(pb);
-                    // advance whichever trajectory is behind until both stand on the same bit
-                    while (pa < my_hi && ca < max_syms && !(has_old && pa == pb)) {
-                        if (!has_old || pa < pb || pb >= my_hi) {
-                            ca += decode_one(sm, br, pa, &d) >= 0;
-                        } else {
-                            cb += decode_one(sm, old, pb, &d) >= 0;
-                        }
+        // ---- stage the payload into shared memory as big-endian words (coalesced 16-byte
+        // loads, bytes past `avail` read as zero), then run the decode phases on it
+        const uint64_t base16 = pay0 & ~uint64_t(15);
+        const uint64_t span_bits = (uint64_t)sub * kDecThreads;           // bits the threads cover
+        const uint64_t want_bytes = (pay0 - base16) + min((span_bits + 7) >> 3, a.avail - pay0) + 8;
+        const uint64_t want_chunks = (want_bytes + 15) >> 4;
+        const bool staged = want_chunks * 16 + 16 <= a.stage_cap &&
+                            (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+        if (staged) {
+            uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
+            for (uint32_t c = tid; c < (uint32_t)want_chunks; c += kDecThreads) {
+                const uint64_t byte = base16 + 16ull * c;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (byte + 16 <= a.avail) {
+                    v = ld_stream_u4(a.in + byte);
+                } else if (byte < a.avail) {
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    for (int q = 0; q < 16; q++) {
+                        if (byte + q < a.avail) w[q >> 2] |= (uint32_t)a.in[byte + q] << (8 * (q & 3));
                     }
-                    if (has_old && pa == pb && pa < my_hi && ca < max_syms) {
-                        cnt = ca + (cnt - cb);  // merged: the rest of the old walk is reused
-                    } else {
-                        cnt = ca;               // ran to the boundary on its own
-                        end = pa;
-                    }
-                    start = want;
+                    v = make_uint4(w[0], w[1], w[2], w[3]);
                 }
-                sm.sub_end[tid] = end;
+                reinterpret_cast<uint4 *>(sw)[c] =
+                    make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
             }
-            if (!__syncthreads_or(redo)) break;
+            if (tid == 0) {  // one spare word so that window() may read index + 1
+                sw[want_chunks * 4] = 0;
+            }
+            __syncthreads();
+            Bits<true> bits;
+            bits.sw = sw;
+            bits.bias = (uint32_t)(8 * (pay0 - base16));
+            bits.last_word = (uint32_t)(want_chunks * 4 - 1);
+            bits.in = a.in;
+            bits.avail = a.avail;
+            bits.pay0 = pay0;
+            decode_phases<true>(sm, bits, a, j, orig_len, doomed, room_bits, sub);
+        } else {
+            Bits<false> bits;
+            bits.sw = nullptr;
+            bits.bias = 0;
+            bits.last_word = 0;
+            bits.in = a.in;
+            bits.avail = a.avail;
+            bits.pay0 = pay0;
+            decode_phases<false>(sm, bits, a, j, orig_len, doomed, room_bits, sub);
         }
-
-        // phase 3: symbol-count scan -> output index of every sub-block
-        const uint32_t incl = warp_incl_scan(cnt);
-        if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            const uint32_t t = tid < kDecThreads / 32 ? sm.warp_tot[tid] : 0;
-            const uint32_t ti = warp_incl_scan(t);
-            if (tid < kDecThreads / 32) sm.warp_tot[tid] = ti - t;
-        }
-        __syncthreads();
-        const uint64_t before = (uint64_t)sm.warp_tot[tid >> 5] + incl - cnt;  // symbols before mine
-        if (tid == kDecThreads - 1) sm.total_syms = before + cnt;
-
-        const uint64_t out0 = a.out_off[j];
-        const bool can_write = !a.count_only && !doomed && out0 + orig_len <= a.out_cap;
-        const bool use_stage = can_write && orig_len <= a.stage_cap;
-
-        // phase 4: every start is proven now: decode for real.  A dead walk met on the way is
-        // an error of the stream, not of the speculation, so sub-blocks in front of the
-        // block's last symbol are walked to their very end even if they hold no symbol.
-        if (before < orig_len && start < end) {
-            const bool finisher = before + cnt >= orig_len;  // the block completes in here
-            const uint32_t need = finisher ? (uint32_t)(orig_len - before) : 0xffffffffu;
-            const uint32_t limit = finisher ? 0xffffffffu : end;
-            uint8_t *dst = !can_write ? nullptr : use_stage ? stage + before : a.out + out0 + before;
-            uint32_t got, dead;
-            br.seek(start);
-            const uint32_t e2 = emit_span(sm, br, start, limit, need, dst, &got, &dead);
-            if (dead != 0xffffffffu) atomicMin(&sm.err_pos, dead);
-            if (finisher) sm.end_bit = e2;
-        }
-        __syncthreads();
 
         // The guessed extent was short (the next candidate was a false positive inside this
         // payload) or the block cannot complete: the chain runs past the last sub-block, whose
-        // end is proven by now, and one thread walks on serially.  Rare by construction.
+        // end is proven by now, and one thread walks on serially from global memory.  Rare.
         if (tid == 0 && sm.total_syms < orig_len) {
             const uint32_t from = sm.sub_end[kDecThreads - 1];
             const uint64_t have = sm.total_syms;
             const uint64_t rest = orig_len - have;
-            uint32_t e2 = from, dead = 0xffffffffu, got = 0;
-            if (from < room_bits) {
-                const uint32_t lim_syms = rest > 0xffffffffull ? 0xffffffffu : (uint32_t)rest;
-                uint8_t *dst = !can_write ? nullptr : use_stage ? stage + have : a.out + out0 + have;
-                br.seek(from);
-                e2 = emit_span(sm, br, from, room_bits, lim_syms, dst, &got, &dead);
+            const uint64_t out0 = a.out_off[j];
+            const bool can_write = !a.count_only && !doomed && out0 + orig_len <= a.out_cap;
+            Bits<false> bits;
+            bits.sw = nullptr;
+            bits.bias = 0;
+            bits.last_word = 0;
+            bits.in = a.in;
+            bits.avail = a.avail;
+            bits.pay0 = pay0;
+            uint32_t pos = from, got = 0, dead = 0xffffffffu;
+            uint8_t *dst = can_write ? a.out + out0 + have : nullptr;
+            while (pos < room_bits && got < rest) {
+                uint32_t d = 0;
+                const int sy = decode_one(sm, bits, pos, &d);
+                if (sy >= 0) {
+                    if (dst) dst[got] = (uint8_t)sy;
+                    got++;
+                } else if (dead == 0xffffffffu) {
+                    dead = d;
+                }
             }
             if (dead != 0xffffffffu) atomicMin(&sm.err_pos, dead);
             if (got == rest) {
-                sm.end_bit = e2;
+                sm.end_bit = pos;
             } else {
                 atomicMin(&sm.err_pos, room_bits);  // ran out of readable bytes
             }
@@ -830,32 +886,6 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         } else if (sm.end_bit > room_bits) {
             // the finishing code word extends past the readable bytes
             status = room_clipped ? kErrFatal : kErrIO;
-        }
-
-        // ---- output: staged blocks leave through coalesced 16-byte stores
-        if (status == kOk && use_stage) {
-            uint8_t *dst = a.out + out0;
-            const uint32_t n = (uint32_t)orig_len;
-            const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
-            for (uint32_t i = tid; i < head; i += kDecThreads) dst[i] = stage[i];
-            const uint32_t body = (n - head) >> 4;
-            if ((head & 3) == 0) {
-                for (uint32_t i = tid; i < body; i += kDecThreads) {
-                    const uint32_t *s = reinterpret_cast<const uint32_t *>(stage + head + 16 * i);
-                    reinterpret_cast<uint4 *>(dst + head)[i] = make_uint4(s[0], s[1], s[2], s[3]);
-                }
-            } else {
-                for (uint32_t i = tid; i < body; i += kDecThreads) {
-                    const uint8_t *s = stage + head + 16 * i;
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        w[q] = s[4 * q] | (s[4 * q + 1] << 8) | (s[4 * q + 2] << 16) |
-                               ((uint32_t)s[4 * q + 3] << 24);
-                    reinterpret_cast<uint4 *>(dst + head)[i] = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-            for (uint32_t i = head + (body << 4) + tid; i < n; i += kDecThreads) dst[i] = stage[i];
         }
         if (tid == 0) {
             a.blk_status[j] = status;

@@ -108,7 +108,7 @@ struct huf_b200_ctx {
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
     uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode
-    uint64_t dec_stage_want = 65536;
+    uint64_t dec_stage_want = 80 * 1024;  // payload bytes of one block staged in shared memory
 };
 
 namespace {
@@ -438,7 +438,7 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     CTX_LAUNCH(c, k_gather, c->sm_count * 4, 256, 0, st, a);
     CTX_LAUNCH(c, k_scan_olen, 1, kScanThreads, 0, st, a);
     if (!plan_only) {
-        // dynamic shared memory: output staging for one block (adapts to the stream's block size)
+        // dynamic shared memory: payload staging for one block (adapts to the stream's block size)
         uint64_t want = c->dec_stage_want;
         const uint64_t static_smem = sizeof(DecSmem) + 1024;
         const uint64_t max_dyn = (uint64_t)c->max_smem_optin > static_smem
@@ -521,7 +521,7 @@ huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_
             if (e != HUF_ERROR_SUCCESS) return e;
             continue;
         }
-        if (r[7] > c->dec_stage_want) c->dec_stage_want = r[7];  // adapt staging to block size
+        if (r[9] + 64 > c->dec_stage_want) c->dec_stage_want = r[9] + 64;  // adapt staging to block size
         *out_len = r[4];
         if (consumed) *consumed = r[3];
         if (r[5]) return (huf_error_t)r[2];
@@ -571,7 +571,7 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
     CU_TRY(cudaMemcpy(&total, a.out_off + n, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     *out_len = total;
     if (nblocks) *nblocks = n;
-    if (c->h_result[7] > c->dec_stage_want) c->dec_stage_want = c->h_result[7];
+    if (c->h_result[9] + 64 > c->dec_stage_want) c->dec_stage_want = c->h_result[9] + 64;
     return HUF_ERROR_SUCCESS;
 }
 

@@ -310,6 +310,10 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31));
 }
+inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    return (uint32_t)(((((uint64_t)hi << 32) | lo) << (sh & 31)) >> 32);
+}
 inline uint32_t __vcmpeq4(uint32_t a, uint32_t b)
 {
     uint32_t r = 0;
