@@ -307,6 +307,7 @@ constexpr int kMaxElems = 1040;   // serialised tree elements (<= 1025) padded
 struct DecSmem {
     int16_t elems[kMaxElems];    // serialised tree as read from the stream; node id == element index
     int16_t open[kMaxElems];     // open child slots before element i is consumed (1 for i == 0)
+    int16_t open_min[kMaxElems / 32 + 2];  // minimum of open[] per aligned run of 32 elements
     int16_t lch[kMaxElems];      // child node ids, -1 = absent
     int16_t rch[kMaxElems];
     int16_t rraw[kMaxElems];     // element index that fills the right slot (-1: elements ran out)
@@ -351,12 +352,17 @@ struct Bits {
     uint64_t avail;
     uint64_t pay0;
 
+    // 32 stream bits starting at payload bit `pos`.  CLAMP = false is for callers that keep
+    // pos inside the staged extent by construction.
+    template <bool CLAMP = true>
     __device__ __forceinline__ uint32_t window(uint32_t pos) const
     {
         if (SMEM) {
             const uint32_t p = pos + bias;
-            const uint32_t i = min(p >> 5, last_word);
-            return __funnelshift_l(sw[i + 1], sw[i], p & 31);
+            uint32_t byte = (p >> 3) & ~3u;
+            if (CLAMP) byte = min(byte, last_word << 2);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(sw) + byte);
+            return __funnelshift_l(w[1], w[0], p & 31);
         }
         const uint64_t byte = pay0 + (pos >> 3);
         uint64_t v = 0;
@@ -373,11 +379,11 @@ struct Bits {
 // -1 when the walk dies: then `pos` advances by one bit (any deterministic rule works for a
 // speculative start; on a proven start the caller records the error) and *dead_at is the bit
 // whose consumption walks into the absent child.
-template <bool SMEM>
+template <bool SMEM, bool CLAMP = true>
 __device__ __forceinline__ int decode_one(const DecSmem &sm, const Bits<SMEM> &bits, uint32_t &pos,
                                           uint32_t *dead_at)
 {
-    const uint16_t e = sm.lut[bits.window(pos) >> (32 - kLutBits)];
+    const uint16_t e = sm.lut[bits.template window<CLAMP>(pos) >> (32 - kLutBits)];
     if (!(e & (kLutLong | kLutDead))) {
         pos += e >> 8;
         return e & 0xff;
@@ -407,14 +413,13 @@ __device__ __forceinline__ int decode_one(const DecSmem &sm, const Bits<SMEM> &b
     }
 }
 
-// Count symbols from `pos` until the position reaches `limit` or `max_syms` symbols were seen.
+// Count symbols from `pos` until the position reaches `limit` (inside the staged extent).
 template <bool SMEM>
 __device__ __forceinline__ uint32_t count_span(const DecSmem &sm, const Bits<SMEM> &bits,
-                                               uint32_t pos, uint32_t limit, uint32_t max_syms,
-                                               uint32_t *end)
+                                               uint32_t pos, uint32_t limit, uint32_t *end)
 {
     uint32_t n = 0, d;
-    while (pos < limit && n < max_syms) n += decode_one(sm, bits, pos, &d) >= 0;
+    while (pos < limit) n += decode_one<SMEM, false>(sm, bits, pos, &d) >= 0;
     *end = pos;
     return n;
 }
@@ -470,11 +475,9 @@ __device__ __forceinline__ void decode_phases(DecSmem &sm, const Bits<SMEM> &bit
     const int tid = threadIdx.x;
     const uint32_t my_lo = (uint32_t)min((uint64_t)tid * sub, (uint64_t)room_bits);
     const uint32_t my_hi = (uint32_t)min((uint64_t)(tid + 1) * sub, (uint64_t)room_bits);
-    const uint32_t max_syms = doomed ? 0xffffffffu : (uint32_t)orig_len;
-
     // phase 1: speculative count of every sub-block from its nominal start
     uint32_t start = my_lo, end = my_lo, cnt = 0;
-    if (my_lo < my_hi) cnt = count_span(sm, bits, start, my_hi, max_syms, &end);
+    if (my_lo < my_hi) cnt = count_span(sm, bits, start, my_hi, &end);
     sm.sub_end[tid] = end;
     __syncthreads();
 
@@ -494,14 +497,14 @@ __device__ __forceinline__ void decode_phases(DecSmem &sm, const Bits<SMEM> &bit
                 const bool has_old = start < my_hi;
                 uint32_t pa = want, pb = start, ca = 0, cb = 0, d;
                 // advance whichever trajectory is behind until both stand on the same bit
-                while (pa < my_hi && ca < max_syms && !(has_old && pa == pb)) {
+                while (pa < my_hi && !(has_old && pa == pb)) {
                     if (!has_old || pa < pb || pb >= my_hi) {
-                        ca += decode_one(sm, bits, pa, &d) >= 0;
+                        ca += decode_one<SMEM, false>(sm, bits, pa, &d) >= 0;
                     } else {
-                        cb += decode_one(sm, bits, pb, &d) >= 0;
+                        cb += decode_one<SMEM, false>(sm, bits, pb, &d) >= 0;
                     }
                 }
-                if (has_old && pa == pb && pa < my_hi && ca < max_syms) {
+                if (has_old && pa == pb && pa < my_hi) {
                     cnt = ca + (cnt - cb);  // merged: the rest of the old walk is reused
                 } else {
                     cnt = ca;               // ran to the boundary on its own
@@ -657,6 +660,17 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         __syncthreads();
         const uint32_t n_eff = sm.n_eff;
 
+        // minimum of open[] over every aligned run of 32 elements: the right-child search
+        // below skips whole runs that cannot contain its target
+        for (uint32_t blk = tid >> 5; blk * 32 < n_eff; blk += kDecThreads / 32) {
+            const uint32_t i = blk * 32 + (tid & 31);
+            int v = i < n_eff ? (int)sm.open[i] : 0x7fff;
+#pragma unroll
+            for (int dd = 16; dd; dd >>= 1) v = min(v, __shfl_xor_sync(kFull, v, dd));
+            if ((tid & 31) == 0) sm.open_min[blk] = (int16_t)v;
+        }
+        __syncthreads();
+
         // children: left slot is filled by the next element; the right slot by the first later
         // element that sees the same number of open slots as this node did.
         for (uint32_t i = tid; i < n_eff; i += kDecThreads) {
@@ -665,7 +679,12 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
                 if (i + 1 < n_eff && sm.elems[i + 1] != -1) l = (int)(i + 1);
                 const int want = sm.open[i];
                 uint32_t k = i + 2;
-                while (k < n_eff && sm.open[k] > want) k++;
+                // finish the current run of 32, then hop over runs whose minimum is too high
+                while (k < n_eff && (k & 31) && sm.open[k] > want) k++;
+                if (k < n_eff && (k & 31) == 0 && sm.open[k] > want) {
+                    while (k < n_eff && sm.open_min[k >> 5] > want) k += 32;
+                    while (k < n_eff && sm.open[k] > want) k++;
+                }
                 if (k < n_eff && i + 1 < n_eff) {
                     rr = (int)k;
                     if (sm.elems[k] != -1) r = (int)k;
