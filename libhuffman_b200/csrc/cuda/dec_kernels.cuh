@@ -470,11 +470,13 @@ __device__ __forceinline__ uint32_t emit_span(const DecSmem &sm, const Bits<SMEM
 template <bool SMEM>
 __device__ __forceinline__ void decode_phases(DecSmem &sm, const Bits<SMEM> &bits, const DecArgs &a,
                                               uint64_t j, uint64_t orig_len, bool doomed,
-                                              uint32_t room_bits, uint32_t sub)
+                                              uint32_t cover_bits, uint32_t sub)
 {
     const int tid = threadIdx.x;
-    const uint32_t my_lo = (uint32_t)min((uint64_t)tid * sub, (uint64_t)room_bits);
-    const uint32_t my_hi = (uint32_t)min((uint64_t)(tid + 1) * sub, (uint64_t)room_bits);
+    // sub-blocks tile the guessed extent only: what lies behind it is the next block's header,
+    // which this block's table would chew through one dead bit at a time
+    const uint32_t my_lo = (uint32_t)min((uint64_t)tid * sub, (uint64_t)cover_bits);
+    const uint32_t my_hi = (uint32_t)min((uint64_t)(tid + 1) * sub, (uint64_t)cover_bits);
     // phase 1: speculative count of every sub-block from its nominal start
     uint32_t start = my_lo, end = my_lo, cnt = 0;
     if (my_lo < my_hi) cnt = count_span(sm, bits, start, my_hi, &end);
@@ -815,8 +817,8 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         // ---- stage the payload into shared memory as big-endian words (coalesced 16-byte
         // loads, bytes past `avail` read as zero), then run the decode phases on it
         const uint64_t base16 = pay0 & ~uint64_t(15);
-        const uint64_t span_bits = (uint64_t)sub * kDecThreads;           // bits the threads cover
-        const uint64_t want_bytes = (pay0 - base16) + min((span_bits + 7) >> 3, a.avail - pay0) + 8;
+        const uint32_t cover_bits = guess_bits;                          // bits the threads cover
+        const uint64_t want_bytes = (pay0 - base16) + min(((uint64_t)cover_bits + 7) >> 3, a.avail - pay0) + 8;
         const uint64_t want_chunks = (want_bytes + 15) >> 4;
         const bool staged = want_chunks * 16 + 16 <= a.stage_cap &&
                             (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
@@ -848,7 +850,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             bits.in = a.in;
             bits.avail = a.avail;
             bits.pay0 = pay0;
-            decode_phases<true>(sm, bits, a, j, orig_len, doomed, room_bits, sub);
+            decode_phases<true>(sm, bits, a, j, orig_len, doomed, cover_bits, sub);
         } else {
             Bits<false> bits;
             bits.sw = nullptr;
@@ -857,7 +859,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             bits.in = a.in;
             bits.avail = a.avail;
             bits.pay0 = pay0;
-            decode_phases<false>(sm, bits, a, j, orig_len, doomed, room_bits, sub);
+            decode_phases<false>(sm, bits, a, j, orig_len, doomed, cover_bits, sub);
         }
 
         // The guessed extent was short (the next candidate was a false positive inside this

@@ -346,7 +346,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpy
 enum { cudaStreamNonBlocking = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 struct cudaDeviceProp {
-    int major = 10, minor = 0, multiProcessorCount = 4;
+    int major = 10, minor = 0, multiProcessorCount = 1;
     size_t sharedMemPerBlockOptin = 227 * 1024;
 };
 
