@@ -313,12 +313,13 @@ struct DecSmem {
     int16_t rraw[kMaxElems];     // element index that fills the right slot (-1: elements ran out)
     uint16_t pre[kMaxElems];     // code prefix (depth bits) of nodes at depth <= kLutBits
     uint8_t lvl[kMaxElems];      // depth of the node, 0xff = deeper than the table or unused
-    uint16_t lut[kLutSize];
+    uint16_t lut[kLutSize + 2];  // [kLutSize] = sentinel: first bit walks off a one-child root
     uint32_t sub_end[kDecThreads + 1];
     uint32_t warp_tot[kDecThreads / 32];
     uint32_t n_term;
     uint32_t n_wide;
     uint32_t n_eff;              // elements that belong to the tree
+    uint32_t skip;               // 1: the root has only a left child, the table starts below it
     int32_t root;
     uint32_t hdr_status;
     uint32_t tree_len;
@@ -348,6 +349,7 @@ struct Bits {
     const uint32_t *sw;   // staged words
     uint32_t bias;        // bits between staged bit 0 and payload bit 0
     uint32_t last_word;   // highest index that may be read (words beyond read as the last one)
+    uint32_t lshift;      // 32 - kLutBits - skip: table index = window >> lshift, capped at kLutSize
     const uint8_t *in;    // whole stream (global)
     uint64_t avail;
     uint64_t pay0;
@@ -383,7 +385,10 @@ template <bool SMEM, bool CLAMP = true>
 __device__ __forceinline__ int decode_one(const DecSmem &sm, const Bits<SMEM> &bits, uint32_t &pos,
                                           uint32_t *dead_at)
 {
-    const uint16_t e = sm.lut[bits.template window<CLAMP>(pos) >> (32 - kLutBits)];
+    // a root with only a left child (every tree the reference encoder emits) costs one bit
+    // per code word that carries no information: the table is indexed behind it, and a set
+    // first bit lands on the sentinel entry
+    const uint16_t e = sm.lut[min(bits.template window<CLAMP>(pos) >> bits.lshift, (uint32_t)kLutSize)];
     if (!(e & (kLutLong | kLutDead))) {
         pos += e >> 8;
         return e & 0xff;
@@ -395,7 +400,7 @@ __device__ __forceinline__ int decode_one(const DecSmem &sm, const Bits<SMEM> &b
     }
     // long code: continue bit by bit from the node reached after kLutBits bits
     int node = e & 0x7ff;
-    uint32_t p = pos + kLutBits;
+    uint32_t p = pos + (32 - bits.lshift);
     for (;;) {
         const int bit = bits.window(p) >> 31;
         const int nx = bit ? sm.rch[node] : sm.lch[node];
@@ -696,18 +701,31 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             sm.rch[i] = (int16_t)r;
             sm.rraw[i] = (int16_t)rr;
         }
-        if (tid == 0 && n_eff > 0 && sm.elems[0] != -1) {
-            sm.root = 0;
-            sm.lvl[0] = 0;
-            sm.pre[0] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            sm.skip = 0;
+            sm.lut[kLutSize] = kLutDead | 1;
+            if (n_eff > 0 && sm.elems[0] != -1) {
+                sm.root = 0;
+                if (sm.lch[0] >= 0 && sm.rch[0] < 0) {
+                    sm.skip = 1;              // table root = the only child, one bit down
+                    sm.lvl[sm.lch[0]] = 1;
+                    sm.pre[sm.lch[0]] = 0;
+                } else {
+                    sm.lvl[0] = 0;
+                    sm.pre[0] = 0;
+                }
+            }
         }
         __syncthreads();
+        const uint32_t skip = sm.skip;
 
         // depth-limited expansion, one level per round: leaves and absent children become
         // table terminals, inner nodes at the table depth become long-code continuations.
         Terminal *term = reinterpret_cast<Terminal *>(stage);
         uint16_t *wide = reinterpret_cast<uint16_t *>(stage + sizeof(Terminal) * (2 * kMaxElems + 8));
-        for (uint32_t d = 0; d <= (uint32_t)kLutBits; d++) {
+        for (uint32_t d = skip; d <= (uint32_t)kLutBits + skip; d++) {
+            const uint32_t de = d - skip;  // depth below the table root
             for (uint32_t i = tid; i < n_eff; i += kDecThreads) {
                 if (sm.lvl[i] != d) continue;
                 const uint32_t p = sm.pre[i];
@@ -717,15 +735,15 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
                 Terminal t[2];
                 if (leaf) {
                     if (d >= 1) {
-                        t[0].start = (uint16_t)(p << (kLutBits - d));
+                        t[0].start = (uint16_t)(p << (kLutBits - de));
                         t[0].entry = (uint16_t)((d << 8) | (uint8_t)sm.elems[i]);
-                        t[0].depth = (uint16_t)d;
+                        t[0].depth = (uint16_t)de;
                         n_new = 1;
                     }  // a root without children keeps the all-dead table
-                } else if (d == (uint32_t)kLutBits) {
+                } else if (de == (uint32_t)kLutBits) {
                     t[0].start = (uint16_t)p;
                     t[0].entry = (uint16_t)(kLutLong | i);
-                    t[0].depth = (uint16_t)d;
+                    t[0].depth = (uint16_t)de;
                     n_new = 1;
                 } else {
                     const int kids[2] = {l, r};
@@ -737,9 +755,9 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
                             sm.pre[kids[side]] = (uint16_t)cp;
                         } else {
                             // consuming this bit walks into an absent child
-                            t[n_new].start = (uint16_t)(cp << (kLutBits - d - 1));
+                            t[n_new].start = (uint16_t)(cp << (kLutBits - de - 1));
                             t[n_new].entry = (uint16_t)(kLutDead | (d + 1));
-                            t[n_new].depth = (uint16_t)(d + 1);
+                            t[n_new].depth = (uint16_t)(de + 1);
                             n_new++;
                         }
                     }
@@ -847,6 +865,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             bits.sw = sw;
             bits.bias = (uint32_t)(8 * (pay0 - base16));
             bits.last_word = (uint32_t)(want_chunks * 4 - 1);
+            bits.lshift = 32 - kLutBits - skip;
             bits.in = a.in;
             bits.avail = a.avail;
             bits.pay0 = pay0;
@@ -856,6 +875,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             bits.sw = nullptr;
             bits.bias = 0;
             bits.last_word = 0;
+            bits.lshift = 32 - kLutBits - skip;
             bits.in = a.in;
             bits.avail = a.avail;
             bits.pay0 = pay0;
@@ -875,6 +895,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
             bits.sw = nullptr;
             bits.bias = 0;
             bits.last_word = 0;
+            bits.lshift = 32 - kLutBits - skip;
             bits.in = a.in;
             bits.avail = a.avail;
             bits.pay0 = pay0;
