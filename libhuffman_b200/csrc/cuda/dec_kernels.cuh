@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
                 uint32_t pre = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    // bytes at offsets 11+4j .. 14+4j
-                    const uint32_t w = __funnelshift_r(d[2 + j], d[3 + j], 24);
-                    const uint32_t eq = __vcmpeq4(w, 0x01010101u);  // 0xff per matching byte
+                    // tree[0] high byte (offsets 11+4j .. 14+4j) must be 0x01 and the tree_len
+                    // high byte (offsets 9+4j .. 12+4j) at most 0x04: 1 in 13000 random offsets
+                    const uint32_t w11 = __funnelshift_r(d[2 + j], d[3 + j], 24);
+                    const uint32_t w9 = __funnelshift_r(d[2 + j], d[3 + j], 8);
+                    const uint32_t eq = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
                     pre |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u))
                            << (4 * j);
                 }
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
         }
         const uint32_t n = __popc(mask);
         total += n;
-        if (EMIT) {
+        if (EMIT && __any_sync(kFull, mask != 0)) {
             // ordered emit: lanes in order, offsets in order inside a lane
             const uint32_t incl = warp_incl_scan(n);
             uint64_t at = wr + incl - n;
@@ -412,7 +414,8 @@ __device__ __forceinline__ int decode_one(const DecSmem &sm, const Bits<SMEM> &b
         p++;
         node = nx;
         if (sm.lch[node] < 0 && sm.rch[node] < 0) {
-            pos = p;
+            // keep the caller inside the staged extent even on a runaway (corrupt) walk
+            pos = SMEM ? min(p, (bits.last_word << 5) - bits.bias - 64) : p;
             return (uint8_t)sm.elems[node];
         }
     }
@@ -441,7 +444,7 @@ __device__ __forceinline__ uint32_t emit_span(const DecSmem &sm, const Bits<SMEM
     uint32_t n = 0, first_dead = 0xffffffffu;
     auto one = [&]() -> uint32_t {
         uint32_t d = 0;
-        const int sy = decode_one(sm, bits, pos, &d);
+        const int sy = decode_one<SMEM, false>(sm, bits, pos, &d);
         if (sy < 0 && first_dead == 0xffffffffu) first_dead = d;
         return (uint32_t)sy & 0xffu;
     };
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
         // loads, bytes past `avail` read as zero), then run the decode phases on it
         const uint64_t base16 = pay0 & ~uint64_t(15);
         const uint32_t cover_bits = guess_bits;                          // bits the threads cover
-        const uint64_t want_bytes = (pay0 - base16) + min(((uint64_t)cover_bits + 7) >> 3, a.avail - pay0) + 8;
+        const uint64_t want_bytes = (pay0 - base16) + (((uint64_t)cover_bits + 7) >> 3) + 64;  // + slack for unclamped windows
         const uint64_t want_chunks = (want_bytes + 15) >> 4;
         const bool staged = want_chunks * 16 + 16 <= a.stage_cap &&
                             (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;

@@ -321,6 +321,14 @@ inline uint32_t __vcmpeq4(uint32_t a, uint32_t b)
         if (((a >> (8 * i)) & 0xff) == ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
     return r;
 }
+inline uint32_t __vcmpleu4(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+        if (((a >> (8 * i)) & 0xff) <= ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
+    return r;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 
