@@ -101,6 +101,10 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *ctx, const void *d_in, uint64_t
 
 /* Counters for benches/tests: kernels launched by the last *_async call. */
 uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx);
+/* After decode_finish: candidate blocks of the last pass that the fast decode lane declined
+ * and the general lane decoded (foreign tree shapes, code words beyond the table reach,
+ * corrupt or truncated blocks, speculative header candidates that are no blocks). */
+uint64_t huf_b200_last_slow_blocks(const huf_b200_ctx_t *ctx);
 
 /* With HUF_B200_OPT_KERNEL_TIMING on: writes one "kernel_name milliseconds\n" line per launch
  * of the last call into buf (NUL terminated). */

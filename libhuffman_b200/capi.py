@@ -175,6 +175,8 @@ class B200Lib(HuffmanCLib):
         d.huf_b200_decode_plan.argtypes = [vp, vp, u64, u64, C.POINTER(u64), C.POINTER(u64), vp]
         d.huf_b200_last_launch_count.restype = u64
         d.huf_b200_last_launch_count.argtypes = [vp]
+        d.huf_b200_last_slow_blocks.restype = u64
+        d.huf_b200_last_slow_blocks.argtypes = [vp]
         d.huf_b200_kernel_times.argtypes = [vp, C.c_char_p, u64]
         d.huf_b200_kernel_times.restype = C.c_int
         d.huf_b200_dev_alloc.argtypes = [C.POINTER(vp), u64]
@@ -251,6 +253,10 @@ class DeviceCodec:
 
     def launches(self) -> int:
         return self.lib.dll.huf_b200_last_launch_count(self.ctx)
+
+    def slow_blocks(self) -> int:
+        """Candidate blocks of the last decode pass that took the general (slow) lane."""
+        return self.lib.dll.huf_b200_last_slow_blocks(self.ctx)
 
     def set_kernel_timing(self, on: bool) -> None:
         self.lib.check(self.lib.dll.huf_b200_ctx_set_option(self.ctx, 2, int(on)), "set_option")

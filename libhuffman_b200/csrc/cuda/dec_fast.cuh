@@ -1,0 +1,657 @@
+// dec_fast.cuh — the fast lane of the decode path (sm_100a).
+//
+//   K4d k_tree     one LANE per candidate block (32 headers staged in shared memory per warp
+//                  with coalesced loads): serial pre-order walk of the serialised tree (grammar
+//                  of reference src/tree.c:138-208) with a small stack, producing the ordered
+//                  list of lookup-table terminals (leaf / absent child / long-code prefix) and
+//                  the shortest code length; leaves below the table reach (13 bits) become
+//                  sorted (code, length, symbol) records that the decoder searches.  Only the
+//                  shape every reference encoder emits is eligible: a root with a left child
+//                  only (src/tree.c:410-413), codes of at most 32 bits.  Anything else --
+//                  foreign tree shapes, broken headers, zero-length blocks -- is left to
+//                  k_decode_slow, which implements the whole acceptance grammar.
+//   K5  k_decode   one CTA per eligible candidate, the block's payload processed in chunks:
+//                  (0) chunk staged in shared memory as big-endian words (coalesced 16-byte loads)
+//                  (1) every thread warms up on the bits in front of its sub-block (Huffman
+//                      codes self-synchronise within ~20 code words), then decodes its sub-block
+//                      and WRITES the symbols into a private shared-memory region (4 symbols per
+//                      32-bit store): no symbol is decoded twice
+//                  (2) verification: a thread's first code word must start where its
+//                      predecessor's last one ended.  The rare thread that did not synchronise
+//                      walks old and new trajectory in lockstep until they meet and rewrites only
+//                      the symbols in front of the meeting point
+//                  (3) symbol-count scan -> output position of every region
+//                  (4) regions compacted into a linear shared buffer (aliasing the stage) and
+//                      copied out with coalesced 16-byte stores.
+//                  Replaces __huf_decode_block (reference src/decoder.c:34-96) for clean blocks.
+//                  A block that shows anything irregular (dead walk on the proven trajectory,
+//                  payload running out) is handed to k_decode_slow untouched, so error codes and
+//                  partial-output behaviour stay those of the general lane.
+#pragma once
+
+#include "dec_kernels.cuh"
+
+namespace hufb200 {
+
+constexpr uint32_t kRedo = kRedoStatus;   // blk_status value: block left to k_decode_slow
+constexpr uint32_t kNone = 0xffffffffu;
+
+// per-candidate scratch slot: table terminals ((table start << 16) | table entry, ascending
+// start) grow from the front, long-code records (left-aligned code, length << 8 | symbol;
+// ascending code) from the back
+constexpr int kTermStride = 800;
+constexpr int kLongMax = 256;
+constexpr int kLongBits = 32;             // longest code word the fast lane handles
+constexpr int kTreeReach = kLutBits + 1;  // code bits resolved by the table incl. the root bit
+
+// Fast-lane table entries (u16): leaf = length << 8 | symbol (length 1..13); the two special
+// kinds carry a length field of 1 so that a walk which only needs to make progress (warm-up)
+// can add bits [11:8] blindly.
+constexpr uint32_t kFastDead = kLutDead | 0x100;  // walks into an absent child
+constexpr uint32_t kFastLong = kLutLong | 0x100;  // code word longer than the table reach
+constexpr uint32_t kFastFlags = 0xc000u;
+
+// two meta words per candidate: [0] bit 0 = eligible for the fast lane, [15:8] shortest code
+// length, [31:16] number of terminals; [1] number of long-code records
+constexpr uint32_t kMetaFast = 1u;
+
+constexpr int kFT = 256;                  // threads per CTA
+constexpr int kRegStride = 252;           // bytes per thread region (63 words: conflict-free)
+constexpr int kRegPad = 12;               // room in front of the speculative symbols
+constexpr int kRegCap = 240;              // symbols a region can hold behind the pad
+constexpr int kMaxSubWords = 29;          // payload words per thread per chunk (odd)
+constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
+constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
+constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
+
+constexpr int kTreeHdrStride = 2068;      // staged header bytes per candidate (517 words, odd)
+constexpr int kTreeDyn = 32 * kTreeHdrStride;
+
+// ------------------------------------------------------------------------------------------
+// K4d: tree walk, one lane per candidate, 32 candidates per CTA.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32) k_tree(DecArgs a)
+{
+#ifdef HUF_EMU
+    uint8_t *hdr = hufemu::dyn_smem();
+#else
+    extern __shared__ __align__(16) uint8_t hdr[];
+#endif
+    const int lane = lane_id();
+    const uint64_t ncand = a.result[0];
+    const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 3) == 0;
+
+    for (uint64_t g0 = (uint64_t)blockIdx.x * 32; g0 < ncand; g0 += (uint64_t)gridDim.x * 32) {
+        __syncwarp();
+        // ---- stage the 32 headers: whole aligned words, copied verbatim
+        uint32_t my_tl = 0, my_skew = 0;
+        uint64_t my_ol = 0;
+        bool my_ok = false;
+        for (int c = 0; c < 32; c++) {
+            const uint64_t j = g0 + c;
+            if (j >= ncand) break;
+            bool ok = in_ok && j < a.term_slots;
+            uint64_t off = 0, ol = 0;
+            uint32_t tl = 0;
+            if (ok) {
+                off = a.cand[j];
+                ok = off + kHdrFixed + 4 <= a.avail;
+            }
+            if (ok) {
+                ol = rd_u64(a.in + off);
+                tl = rd_u16(a.in + off + 8);
+                ok = ol != 0 && tl >= 5 && tl <= (a.accept_1025 ? 1025u : 1024u) &&
+                     off + kHdrFixed + 2ull * tl <= a.avail;
+            }
+            if (ok) {
+                const uint64_t b0 = off + kHdrFixed;
+                const uint64_t w0 = b0 >> 2, w1 = (b0 + 2ull * tl + 3) >> 2;  // word range
+                uint32_t *dst = reinterpret_cast<uint32_t *>(hdr + c * kTreeHdrStride);
+                for (uint64_t k = w0 + lane; k < w1; k += 32) {
+                    uint32_t v = 0;
+                    if (4 * k + 4 <= a.avail) {
+                        v = reinterpret_cast<const uint32_t *>(a.in)[k];
+                    } else {
+                        for (int q = 0; q < 4; q++) {
+                            if (4 * k + q < a.avail) v |= (uint32_t)a.in[4 * k + q] << (8 * q);
+                        }
+                    }
+                    dst[k - w0] = v;
+                }
+                if (c == lane) {
+                    my_skew = (uint32_t)(b0 & 3);
+                    my_tl = tl;
+                    my_ol = ol;
+                }
+            }
+            if (c == lane) my_ok = ok;
+        }
+        __syncwarp();
+
+        // ---- every lane walks its own tree
+        const uint64_t j = g0 + lane;
+        uint32_t meta = 0, nlong = 0;
+        if (j < ncand && my_ok && my_ol) {
+            const uint8_t *el = hdr + lane * kTreeHdrStride + my_skew;
+            const uint32_t tl = my_tl;
+            // elements past tree_len read as absent children (src/tree.c:154-160)
+            auto elem = [&](uint32_t i) -> int {
+                return i < tl ? (int)(int16_t)(el[2 * i] | ((uint32_t)el[2 * i + 1] << 8)) : -1;
+            };
+            uint32_t *slot = a.terms + j * kTermStride;
+            uint32_t stk[kLongBits + 8];  // ancestors whose right slot is pending: element | depth << 16
+            int sp = 0;
+            stk[sp++] = 0;                // the root, depth 0
+            uint32_t i = 1, D = 1;        // slot being filled: depth D ...
+            uint64_t C = 0;               // ... reached by the path bits C
+            uint32_t nterm = 0, min_len = kTreeReach + 1;
+            bool ok = elem(0) != -1 && elem(1) != -1;  // a root with something below its left edge
+            while (ok) {
+                const int e = elem(i);
+                bool pop;
+                if (e != -1) {
+                    if (elem(i + 1) == -1 && elem(i + 2) == -1) {  // leaf: v, absent, absent
+                        const uint32_t entry = (D << 8) | (uint32_t)(e & 0xff);
+                        if (D <= (uint32_t)kTreeReach) {
+                            if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
+                            slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) | entry;
+                            min_len = min(min_len, D);
+                        } else {
+                            if (nlong >= (uint32_t)kLongMax || nterm + 2 * nlong + 3 > (uint32_t)kTermStride) {
+                                ok = false;
+                                break;
+                            }
+                            slot[kTermStride - 2 * (nlong + 1)] = (uint32_t)(C << (kLongBits - D));
+                            slot[kTermStride - 2 * (nlong + 1) + 1] = entry;
+                            nlong++;
+                        }
+                        i += 3;
+                        pop = true;
+                    } else {
+                        if (D >= (uint32_t)kLongBits) {  // leaves below would need more than 32 bits
+                            ok = false;
+                            break;
+                        }
+                        if (D == (uint32_t)kTreeReach) {  // inner node at the table depth: long codes
+                            if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
+                            slot[nterm++] = ((uint32_t)C << 16) | kFastLong;
+                        }
+                        stk[sp++] = i | (D << 16);
+                        i++;
+                        D++;
+                        C <<= 1;
+                        pop = false;
+                    }
+                } else {
+                    // consuming bit D walks into an absent child; below the table such a walk
+                    // simply matches no long-code record
+                    if (D <= (uint32_t)kTreeReach) {
+                        if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
+                        slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) | kFastDead;
+                    }
+                    i++;
+                    pop = true;
+                }
+                if (pop) {
+                    if (sp == 0) break;  // every slot filled: the tree is complete
+                    const uint32_t s = stk[--sp];
+                    const uint32_t d = s >> 16;
+                    C = ((C >> (D - d)) << 1) | 1u;
+                    D = d + 1;
+                    // the right slot of the root must stay empty (table sits behind the root bit)
+                    if (d == 0 && elem(i) != -1) ok = false;
+                }
+            }
+            if (ok) meta = kMetaFast | (min_len << 8) | (nterm << 16);
+        }
+        if (j < ncand) {
+            a.meta[2 * j] = meta;
+            a.meta[2 * j + 1] = nlong;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: fast block decode.
+// ------------------------------------------------------------------------------------------
+
+struct FastSmem {
+    __align__(16) uint16_t lut[kLutSize + 8];  // [kLutSize] = sentinel: root bit set
+    uint32_t sub_end[kFT];
+    uint32_t long_code[kLongMax];  // left-aligned code words longer than the table reach, ascending
+    uint16_t long_ent[kLongMax];   // length << 8 | symbol
+    uint32_t nlong;
+    uint32_t warp_tot[kFT / 32];
+    uint32_t redo;
+    uint32_t fin_found;
+    uint32_t fin_end;
+    uint32_t total;
+};
+
+// Table entry for the code word that starts at staged bit `pos` (stateless: two words + shift).
+__device__ __forceinline__ uint32_t fast_look(const uint32_t *sw, const uint16_t *lut, uint32_t pos)
+{
+    const uint32_t wi = pos >> 5;
+    const uint32_t win = __funnelshift_l(sw[wi + 1], sw[wi], pos);
+    return lut[min(win >> (32 - kTreeReach), (uint32_t)kLutSize)];
+}
+
+// Four consecutive table entries from `pos` on: three staged words are loaded once into a
+// 64-bit left-aligned bit buffer that is shifted by every code length (4 x 13 bits fit).
+// Positions advance by bits [11:8] of each entry.  Returns the position behind the fourth.
+__device__ __forceinline__ uint32_t fast_look4(const uint32_t *sw, const uint16_t *lut, uint32_t pos,
+                                               uint32_t &e0, uint32_t &e1, uint32_t &e2, uint32_t &e3)
+{
+    const uint32_t wi = pos >> 5;
+    const uint32_t w0 = sw[wi], w1 = sw[wi + 1], w2 = sw[wi + 2];
+    uint32_t hi = __funnelshift_l(w1, w0, pos);  // stream bits pos .. pos+31
+    uint32_t lo = __funnelshift_l(w2, w1, pos);  // stream bits pos+32 .. pos+63
+    e0 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
+    const uint32_t l0 = (e0 >> 8) & 0xfu;
+    hi = __funnelshift_l(lo, hi, l0);
+    lo <<= l0;
+    e1 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
+    const uint32_t l1 = (e1 >> 8) & 0xfu;
+    hi = __funnelshift_l(lo, hi, l1);
+    lo <<= l1;
+    e2 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
+    const uint32_t l2 = (e2 >> 8) & 0xfu;
+    hi = __funnelshift_l(lo, hi, l2);
+    e3 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
+    const uint32_t l3 = (e3 >> 8) & 0xfu;
+    return pos + l0 + l1 + l2 + l3;
+}
+
+// One exact decode step at staged bit position `pos`: true + symbol when a code word starts
+// there (table hit or long-code record), false when the walk dies (pos advances one bit: any
+// deterministic rule serves a speculative start, and a dead step on the proven trajectory sends
+// the block to the general lane).
+__device__ __forceinline__ bool fast_step(const uint32_t *sw, const FastSmem &sm, uint32_t &pos,
+                                          uint32_t &sym)
+{
+    const uint32_t wi = pos >> 5;
+    const uint32_t win = __funnelshift_l(sw[wi + 1], sw[wi], pos);
+    const uint32_t e = sm.lut[min(win >> (32 - kTreeReach), (uint32_t)kLutSize)];
+    if (!(e & kFastFlags)) {
+        sym = e & 0xffu;
+        pos += e >> 8;
+        return true;
+    }
+    if (e & kLutLong) {
+        // last record with code <= window; prefix-free codes: it is the only possible match
+        uint32_t lo = 0, hi = sm.nlong;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sm.long_code[mid] <= win) lo = mid; else hi = mid;
+        }
+        if (hi) {
+            const uint32_t ent = sm.long_ent[lo];
+            const uint32_t len = ent >> 8;
+            if (((win ^ sm.long_code[lo]) >> (32 - len)) == 0) {
+                sym = ent & 0xffu;
+                pos += len;
+                return true;
+            }
+        }
+    }
+    pos += 1;
+    return false;
+}
+
+// Copy n bytes between two shared-memory locations of arbitrary alignment, word-wise.
+__device__ __forceinline__ void smem_copy(uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+    while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) {
+        *dst++ = *src++;
+        n--;
+    }
+    if (n >= 4) {
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+        const uint32_t *s = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
+        uint32_t prev = *s;
+        do {
+            const uint32_t next = *++s;
+            *reinterpret_cast<uint32_t *>(dst) = __funnelshift_r(prev, next, sh);
+            prev = next;
+            dst += 4;
+            src += 4;
+            n -= 4;
+        } while (n >= 4);
+    }
+    while (n) {
+        *dst++ = *src++;
+        n--;
+    }
+}
+
+__global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
+{
+#ifdef HUF_EMU
+    uint8_t *dyn = hufemu::dyn_smem();
+#else
+    extern __shared__ __align__(16) uint8_t dyn[];
+#endif
+    __shared__ FastSmem sm;
+    const int tid = threadIdx.x;
+    const uint64_t ncand = a.result[0];
+    uint32_t *sw = reinterpret_cast<uint32_t *>(dyn);  // staged payload, big-endian words
+    uint8_t *regions = dyn + kFastStage;
+    uint8_t *reg = regions + tid * kRegStride;
+    const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+
+    for (uint64_t j = blockIdx.x; j < ncand; j += gridDim.x) {
+        __syncthreads();
+        const uint32_t meta = a.meta[2 * j];
+        const uint32_t nlong = a.meta[2 * j + 1];
+        const uint64_t off = a.cand[j];
+        uint64_t orig_len = 0;
+        uint32_t tl = 0;
+        bool fast = (meta & kMetaFast) && in_ok;
+        if (fast) {
+            orig_len = rd_u64(a.in + off);
+            tl = rd_u16(a.in + off + 8);
+        }
+        const uint64_t pay0 = off + kHdrFixed + 2ull * tl;
+        if (fast && orig_len > 8ull * (a.avail - pay0)) fast = false;  // cannot complete: error lane
+        if (!fast) {
+            if (tid == 0) {
+                a.blk_status[j] = kRedo;
+                atomicAdd(reinterpret_cast<unsigned long long *>(&a.result[10]), 1ull);
+            }
+            continue;
+        }
+        const uint32_t min_len = (meta >> 8) & 0xffu;
+        const uint32_t nterm = meta >> 16;
+
+        // ---- lookup table from the ordered terminal list: every thread fills 16 entries
+        {
+            uint32_t *tb = reinterpret_cast<uint32_t *>(regions);
+            const uint32_t *src = a.terms + j * kTermStride;
+            for (uint32_t k = tid; k < nterm; k += kFT) tb[k] = src[k];
+            for (uint32_t r = tid; r < nlong; r += kFT) {
+                sm.long_code[r] = src[kTermStride - 2 * (r + 1)];
+                sm.long_ent[r] = (uint16_t)src[kTermStride - 2 * (r + 1) + 1];
+            }
+            if (tid == 0) {
+                sm.lut[kLutSize] = (uint16_t)kFastDead;
+                sm.redo = 0;
+                sm.nlong = nlong;
+            }
+            __syncthreads();
+            constexpr int kPer = kLutSize / kFT;  // 16
+            const uint32_t idx0 = (uint32_t)tid * kPer;
+            uint32_t lo = 0, hi = nterm;  // last terminal with start <= idx0 (terminal 0 starts at 0)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if ((tb[mid] >> 16) <= idx0) lo = mid; else hi = mid;
+            }
+            uint32_t k = lo;
+            uint32_t cur = tb[k] & 0xffffu;
+            uint32_t nxt = k + 1 < nterm ? tb[k + 1] >> 16 : kNone;
+            uint32_t w[kPer / 2];
+#pragma unroll
+            for (int q = 0; q < kPer; q++) {
+                if (idx0 + q == nxt) {
+                    k++;
+                    cur = tb[k] & 0xffffu;
+                    nxt = k + 1 < nterm ? tb[k + 1] >> 16 : kNone;
+                }
+                if (q & 1) w[q >> 1] |= cur << 16; else w[q >> 1] = cur;
+            }
+#pragma unroll
+            for (int q = 0; q < kPer / 8; q++) {
+                reinterpret_cast<uint4 *>(sm.lut)[tid * (kPer / 8) + q] =
+                    make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+        }
+        __syncthreads();
+
+        // ---- chunk loop
+        const uint64_t next_cand = (j + 1 < ncand) ? a.cand[j + 1] : a.avail;
+        const uint64_t room_end = 8ull * a.avail;
+        uint64_t guess_end = next_cand < a.avail ? next_cand : a.avail;
+        guess_end = 8ull * (guess_end > pay0 ? guess_end : pay0);
+        bool use_guess = guess_end > 8ull * pay0;
+        uint64_t next_bit = 8ull * pay0;  // absolute stream bit of the next code word (proven)
+        uint64_t produced = 0, end_bit = 0;
+        const uint64_t out0 = a.out_off[j];
+        const bool can_write = !a.count_only && out0 + orig_len <= a.out_cap;
+        uint32_t sub_cap_w = min((uint32_t)kMaxSubWords, (kRegCap * min_len) / 32u);
+        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 7, so never below 7
+        // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
+        uint32_t warm = 160;
+        if (use_guess) {
+            const uint64_t w = 20ull * (guess_end - 8ull * pay0) / orig_len;
+            warm = (uint32_t)(w < 64 ? 64 : (w > 320 ? 320 : w));
+        }
+        uint32_t status = kOk;
+
+        for (;;) {
+            const uint64_t limit = use_guess ? guess_end : room_end;
+            if (next_bit >= limit) {
+                if (use_guess) {
+                    use_guess = false;  // the next candidate sat inside this payload: go on
+                    continue;
+                }
+                status = kRedo;  // out of readable bits before orig_len symbols: error lane
+                break;
+            }
+            const uint64_t base16 = (next_bit >> 3) & ~uint64_t(15);
+            const uint32_t rel_start = (uint32_t)(next_bit - 8ull * base16);
+            const uint32_t A = rel_start & ~31u;
+            const uint64_t span = limit - (8ull * base16 + A);
+            const uint64_t chunk_cap = (uint64_t)kFT * 32u * sub_cap_w;
+            const uint64_t nch = (span + chunk_cap - 1) / chunk_cap;
+            uint32_t subw = (uint32_t)((span + nch * kFT * 32u - 1) / (nch * kFT * 32u));
+            subw |= 1u;
+            if (subw < 7) subw = 7;
+            if (subw > sub_cap_w) subw = sub_cap_w;
+            const uint32_t sub = subw * 32u;
+            const uint64_t lim_rel = limit - 8ull * base16;
+            const uint64_t cov64 = (uint64_t)A + (uint64_t)kFT * sub;
+            const uint32_t cover = (uint32_t)(cov64 < lim_rel ? cov64 : lim_rel);
+
+            // (0) stage the chunk: 16-byte loads, bytes past `avail` read as zero
+            {
+                const uint32_t n16 = ((cover + 7) >> 3) / 16 + 2;
+                for (uint32_t c = tid; c < n16; c += kFT) {
+                    const uint64_t byte = base16 + 16ull * c;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (byte + 16 <= a.avail) {
+                        v = ld_stream_u4(a.in + byte);
+                    } else if (byte < a.avail) {
+                        uint32_t w[4] = {0, 0, 0, 0};
+                        for (int q = 0; q < 16; q++) {
+                            if (byte + q < a.avail) w[q >> 2] |= (uint32_t)a.in[byte + q] << (8 * (q & 3));
+                        }
+                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    reinterpret_cast<uint4 *>(sw)[c] =
+                        make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+                }
+            }
+            __syncthreads();
+
+            // (1) warm-up in front of my sub-block, then decode it into my region
+            const uint32_t my_lo = tid == 0 ? rel_start : min(A + (uint32_t)tid * sub, cover);
+            const uint32_t my_hi = min(A + (uint32_t)(tid + 1) * sub, cover);
+            uint32_t pos = my_lo, cnt = 0, roff = kRegPad, last_dead = kNone;
+            if (tid > 0 && my_lo < my_hi) {
+                // start `warm` bits early (or at the proven chunk start when that is closer)
+                pos = my_lo > rel_start + warm ? my_lo - warm : rel_start;
+                uint32_t e0, e1, e2, e3;
+                while (pos + 4 * kTreeReach <= my_lo) pos = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3);
+                while (pos < my_lo) pos += (fast_look(sw, sm.lut, pos) >> 8) & 0xfu;
+            }
+            uint32_t start = pos;  // first code word of mine (speculative unless tid == 0)
+            if (pos < my_hi) {
+                for (;;) {
+                    while (pos + 4 * kTreeReach <= my_hi && !(cnt & 3)) {
+                        uint32_t e0, e1, e2, e3;
+                        const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3);
+                        if ((e0 | e1 | e2 | e3) & kFastFlags) break;
+                        pos = np;
+                        const uint32_t lo2 = __byte_perm(e0, e1, 0x0040);
+                        const uint32_t hi2 = __byte_perm(e2, e3, 0x0040);
+                        *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = __byte_perm(lo2, hi2, 0x5410);
+                        cnt += 4;
+                    }
+                    if (pos >= my_hi) break;
+                    const uint32_t at = pos;
+                    uint32_t sy;
+                    if (fast_step(sw, sm, pos, sy)) {
+                        reg[kRegPad + cnt] = (uint8_t)sy;
+                        cnt++;
+                    } else {
+                        last_dead = at;
+                    }
+                }
+            }
+            uint32_t end = pos;
+            sm.sub_end[tid] = end;
+            __syncthreads();
+
+            // (2) verification and (rare) sync-point fix-up
+            for (int round = 0; round < kFT; round++) {
+                const uint32_t want = tid == 0 ? start : sm.sub_end[tid - 1];
+                const bool redo = want != start;
+                __syncthreads();
+                if (redo) {
+                    if (want >= my_hi) {
+                        cnt = 0;
+                        end = want;
+                        roff = kRegPad;
+                        last_dead = kNone;
+                    } else {
+                        const bool has_old = start < my_hi;
+                        uint32_t pa = want, pb = start, ca = 0, cb = 0, da = kNone;
+                        while (pa < my_hi && !(has_old && pa == pb)) {
+                            uint32_t sy;
+                            if (!has_old || pa < pb || pb >= my_hi) {
+                                const uint32_t at = pa;
+                                if (fast_step(sw, sm, pa, sy)) ca++; else da = at;
+                            } else {
+                                if (fast_step(sw, sm, pb, sy)) cb++;
+                            }
+                        }
+                        uint32_t wr;  // region offset the new head is written at
+                        if (has_old && pa == pb && pa < my_hi) {
+                            // merged at pa: the old symbols from index cb on stay valid
+                            int32_t nroff = (int32_t)roff + (int32_t)cb - (int32_t)ca;
+                            if (nroff < 0) {
+                                // no room in front: slide the surviving tail to the right
+                                const uint32_t shift = (uint32_t)(-nroff);
+                                for (uint32_t q = cnt; q > cb; q--) reg[roff + q - 1 + shift] = reg[roff + q - 1];
+                                nroff = 0;
+                            }
+                            wr = (uint32_t)nroff;
+                            cnt = ca + (cnt - cb);
+                            last_dead = (last_dead != kNone && last_dead >= pa) ? last_dead : da;
+                        } else {
+                            wr = kRegPad;
+                            cnt = ca;
+                            end = pa;
+                            last_dead = da;
+                        }
+                        roff = wr;
+                        // rewrite the head: the first ca symbols of the new trajectory
+                        uint32_t p = want;
+                        for (uint32_t q = 0; q < ca;) {
+                            uint32_t sy;
+                            if (fast_step(sw, sm, p, sy)) {
+                                reg[wr + q] = (uint8_t)sy;
+                                q++;
+                            }
+                        }
+                    }
+                    start = want;
+                    sm.sub_end[tid] = end;
+                }
+                if (!__syncthreads_or(redo)) break;
+            }
+
+            // (3) symbol-count scan
+            const uint32_t incl = warp_incl_scan(cnt);
+            if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
+            if (tid == 0) sm.fin_found = 0;
+            __syncthreads();
+            if (tid < 32) {
+                const uint32_t t = tid < kFT / 32 ? sm.warp_tot[tid] : 0;
+                const uint32_t ti = warp_incl_scan(t);
+                if (tid < kFT / 32) sm.warp_tot[tid] = ti - t;
+                if (tid == kFT / 32 - 1) sm.total = ti;
+            }
+            __syncthreads();
+            const uint32_t before = sm.warp_tot[tid >> 5] + incl - cnt;
+            const uint32_t total = sm.total;
+            const uint64_t remaining = orig_len - produced;
+            const bool in_blk = (uint64_t)before < remaining && cnt > 0;
+            const bool fin = in_blk && (uint64_t)before + cnt >= remaining;
+            const uint32_t ncopy = in_blk ? (fin ? (uint32_t)(remaining - before) : cnt) : 0;
+            if (in_blk && !fin && last_dead != kNone) sm.redo = 1;  // dead walk on the proven chain
+            if (fin) {
+                // the block ends inside my sub-block: find the bit behind its last code word
+                uint32_t p = start, dead = 0;
+                for (uint32_t q = 0; q < ncopy;) {
+                    uint32_t sy;
+                    if (fast_step(sw, sm, p, sy)) q++; else dead = 1;
+                }
+                if (dead) sm.redo = 1;
+                sm.fin_end = p;
+                sm.fin_found = 1;
+            }
+            __syncthreads();
+            if (sm.redo) {
+                status = kRedo;
+                break;
+            }
+            const bool fin_found = sm.fin_found != 0;
+            const uint32_t total_copy = (uint64_t)total < remaining ? total : (uint32_t)remaining;
+
+            // (4) compaction into the (now free) stage buffer, coalesced copy-out
+            if (can_write && total_copy) {
+                uint8_t *dst0 = a.out + out0 + produced;  // first output byte of this chunk
+                const uint32_t m = (uint32_t)(reinterpret_cast<uintptr_t>(dst0) & 15);
+                uint8_t *obuf = dyn;
+                const uint32_t y0 = m + before, y1 = y0 + ncopy;  // my bytes in aligned position space
+                const uint32_t yend = m + total_copy;
+                for (uint32_t wb = 0; wb < yend; wb += kFastOutWin) {
+                    const uint32_t we = wb + kFastOutWin;
+                    const uint32_t c0 = max(y0, wb), c1 = min(y1, we);
+                    if (c0 < c1) smem_copy(obuf + (c0 - wb), reg + roff + (c0 - y0), c1 - c0);
+                    __syncthreads();
+                    const uint32_t vend = min(yend, we) - wb;          // valid bytes end (window relative)
+                    const uint32_t vbeg = wb == 0 ? m : 0;             // valid bytes begin
+                    uint8_t *gbase = dst0 - m + wb;                    // 16-byte aligned
+                    const uint32_t nlines = (vend + 15) >> 4;
+                    for (uint32_t L = tid; L < nlines; L += kFT) {
+                        const uint32_t b0 = L * 16, b1 = b0 + 16;
+                        if (b0 >= vbeg && b1 <= vend) {
+                            *reinterpret_cast<uint4 *>(gbase + b0) = *reinterpret_cast<const uint4 *>(obuf + b0);
+                        } else {
+                            for (uint32_t q = max(b0, vbeg); q < min(b1, vend); q++) gbase[q] = obuf[q];
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            produced += total_copy;
+            if (fin_found) {
+                end_bit = 8ull * base16 + sm.fin_end;
+                break;
+            }
+            next_bit = 8ull * base16 + sm.sub_end[kFT - 1];
+            __syncthreads();
+        }
+
+        if (status == kOk && end_bit > room_end) status = kRedo;  // last code word leaves the readable bytes
+        if (tid == 0) {
+            a.blk_status[j] = status;
+            a.end_off[j] = (end_bit + 7) >> 3;
+            if (status == kRedo) atomicAdd(reinterpret_cast<unsigned long long *>(&a.result[10]), 1ull);
+        }
+    }
+}
+
+}  // namespace hufb200

@@ -55,6 +55,9 @@ struct DecArgs {
     uint64_t *out_off;     // [max_cand + 1]
     uint64_t *end_off;     // [max_cand]  byte offset just past the block
     uint32_t *blk_status;  // [max_cand]
+    uint32_t *meta;        // [max_cand]  fast-lane eligibility + table facts (dec_fast.cuh)
+    uint32_t *terms;       // [term_slots][kTermStride]  ordered table terminals per candidate
+    uint64_t term_slots;   // candidates that own a terminal slot (the rest take the slow lane)
     uint64_t max_cand;
     uint64_t nchunks;
     uint64_t *result;      // [0] ncand [1] proven blocks [2] status [3] consumed [4] out bytes
@@ -62,6 +65,7 @@ struct DecArgs {
                            // [7] largest orig_len among the candidates
                            // [8] sparse-mode slot overflow (rerun with the two-pass scan)
                            // [9] largest block extent (header + payload bytes) seen
+                           // [10] blocks the fast lane left to k_decode_slow
 };
 
 // ------------------------------------------------------------------------------------------
@@ -567,7 +571,12 @@ __device__ __forceinline__ void decode_phases(DecSmem &sm, const Bits<SMEM> &bit
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
+// The general lane: every block the fast lane (dec_fast.cuh) marked kRedoStatus -- foreign tree
+// shapes, deep trees, corrupt or truncated blocks -- with the full acceptance grammar and the
+// reference's error codes.
+constexpr uint32_t kRedoStatus = 0x80;
+
+__global__ void __launch_bounds__(kDecThreads) k_decode_slow(DecArgs a)
 {
 #ifdef HUF_EMU
     uint8_t *stage = hufemu::dyn_smem();
@@ -577,8 +586,10 @@ __global__ void __launch_bounds__(kDecThreads) k_decode(DecArgs a)
     __shared__ DecSmem sm;
     const int tid = threadIdx.x;
     const uint64_t ncand = a.result[0];
+    if (a.result[10] == 0) return;  // nothing was left over
 
     for (uint64_t j = blockIdx.x; j < ncand; j += gridDim.x) {
+        if (a.blk_status[j] != kRedoStatus) continue;
         __syncthreads();
         const uint64_t off = a.cand[j];
         const uint64_t next_cand = (j + 1 < ncand) ? a.cand[j + 1] : a.avail;

@@ -9,6 +9,7 @@
 #include <huffman/b200.h>
 
 #include "dec_kernels.cuh"
+#include "dec_fast.cuh"
 #include "enc_kernels.cuh"
 
 using namespace hufb200;
@@ -107,7 +108,9 @@ struct huf_b200_ctx {
     bool dec_pending = false;
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
-    uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode
+    uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode_slow
+    bool fast_ready = false;        // k_decode attributes set
+    int fast_per_sm = 1;
     uint64_t dec_stage_want = 80 * 1024;  // payload bytes of one block staged in shared memory
 };
 
@@ -247,6 +250,8 @@ uint64_t huf_b200_encode_bound(uint64_t length, uint64_t blocksize)
 }
 
 uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t huf_b200_last_slow_blocks(const huf_b200_ctx_t *ctx) { return ctx ? ctx->h_result[10] : 0; }
 
 huf_error_t huf_b200_kernel_times(huf_b200_ctx_t *c, char *buf, uint64_t buflen)
 {
@@ -412,7 +417,11 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     need += Arena::padded(a.nchunks * kFindSlots * sizeof(uint32_t));
     need += Arena::padded((a.nchunks + 1) * sizeof(uint64_t));
     need += 4 * Arena::padded((max_cand + 1) * sizeof(uint64_t));
-    need += Arena::padded(max_cand * sizeof(uint32_t));
+    need += 3 * Arena::padded(max_cand * sizeof(uint32_t));
+    // terminal slots of the fast lane: enough for every block of ~1 KiB and larger
+    uint64_t term_slots = span / 1024 + 4096;
+    if (term_slots > max_cand) term_slots = max_cand;
+    need += Arena::padded(term_slots * kTermStride * sizeof(uint32_t));
     if (!c->dec_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
     a.chunk_cnt = c->dec_ws.take<uint32_t>(a.nchunks);
     a.slots = c->dec_ws.take<uint32_t>(a.nchunks * kFindSlots);
@@ -422,6 +431,9 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     a.out_off = c->dec_ws.take<uint64_t>(max_cand + 1);
     a.end_off = c->dec_ws.take<uint64_t>(max_cand + 1);
     a.blk_status = c->dec_ws.take<uint32_t>(max_cand);
+    a.meta = c->dec_ws.take<uint32_t>(2 * max_cand);
+    a.terms = c->dec_ws.take<uint32_t>(term_slots * kTermStride);
+    a.term_slots = term_slots;
     a.result = c->d_result;
 
     CU_TRY(cudaMemsetAsync(c->d_result, 0, 16 * sizeof(uint64_t), st));
@@ -447,16 +459,29 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         if (want < 20480) want = 20480;  // the terminal list of the table build lives here
         want &= ~uint64_t(15);
         if ((uint32_t)want != c->dec_stage) {
-            CU_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CU_TRY(cudaFuncSetAttribute(k_decode_slow, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)want));
             c->dec_stage = (uint32_t)want;
         }
         a.stage_cap = c->dec_stage;
         int per_sm = 1;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode, kDecThreads,
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_slow, kDecThreads,
                                                              c->dec_stage));
         if (per_sm < 1) per_sm = 1;
-        CTX_LAUNCH(c, k_decode, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
+        if (!c->fast_ready) {
+            CU_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFastDyn));
+            int fper = 1;
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fper, k_decode, kFT, kFastDyn));
+            c->fast_per_sm = fper < 1 ? 1 : fper;
+            CU_TRY(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeDyn));
+            c->fast_ready = true;
+        }
+        // fast lane: tree walk (one lane per candidate), chunked region decode; whatever it
+        // declines goes through the general lane
+        CTX_LAUNCH(c, k_tree, c->sm_count * 3, 32, kTreeDyn, st, a);
+        CTX_LAUNCH(c, k_decode, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
+        CTX_LAUNCH(c, k_decode_slow, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
         CTX_LAUNCH(c, k_verify, 1, kScanThreads, 0, st, a);
     }
     CU_TRY(cudaGetLastError());

@@ -129,3 +129,42 @@ def test_emu_short_reader_and_length_semantics(emu, harness):
     assert (rc, got) == (0, data[:400])
     rc, got = emu.decode(stream + b"\x07\x07\x07")
     assert rc == 3 and got == data     # junk after the last whole block: READ_WRITE after the output
+
+
+def _lanes(lib, stream, out_cap, accept_1025=False):
+    """Decode through the device entry points; returns (rc, bytes, slow-lane block count)."""
+    codec = DeviceCodec(lib, accept_1025=accept_1025)
+    try:
+        src = C.create_string_buffer(stream, len(stream) + 16)
+        out = C.create_string_buffer(out_cap + 64)
+        codec.decode_async(C.addressof(src), len(stream), len(stream), C.addressof(out), out_cap + 64)
+        rc, n, used = codec.decode_finish()
+        return rc, out.raw[:n], codec.slow_blocks()
+    finally:
+        codec.close()
+
+
+def _deep_blocks(harness, data, bs, reach=32):
+    """Blocks of oracle_encode(data, bs) whose longest code word exceeds the table reach."""
+    deep = 0
+    step = bs if bs else len(data)
+    for i in range(0, len(data), step):
+        blk = data[i:i + step]
+        lens, _, _ = harness.oracle_codebook([blk.count(bytes([b])) for b in range(256)])
+        deep += max(lens) > reach
+    return deep
+
+
+def test_emu_fast_lane_takes_encoder_shaped_blocks(emu, harness):
+    """Blocks with the reference encoder's tree shape must be decoded by the fast lane (codes
+    beyond the 13-bit table go through its long-code records); only code words beyond 32 bits
+    (and, in strict mode, 1025-element trees) may take the general lane."""
+    for name, data, bs in CASES:
+        stream = harness.oracle_encode(data, bs)
+        rc, got, slow = _lanes(emu, stream, len(data), accept_1025=True)
+        assert (rc, got) == (0, data), name
+        assert slow == _deep_blocks(harness, data, bs), name
+    # strict mode: the 1025-element tree is refused by the general lane like the reference does
+    data = bytes(range(256)) * 3
+    rc, got, slow = _lanes(emu, harness.oracle_encode(data, 0), len(data))
+    assert rc == 5 and slow == 1
