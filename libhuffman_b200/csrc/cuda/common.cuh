@@ -45,6 +45,25 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p)
 #endif
 }
 
+// Asynchronous 4-byte global -> shared copy (LDGSTS): many can be in flight per thread without
+// holding registers; cp_async_wait_all() makes the issuing thread's copies visible to it.
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+#ifdef HUF_EMU
+    *reinterpret_cast<uint32_t *>(smem_dst) = *reinterpret_cast<const uint32_t *>(gsrc);
+#else
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void cp_async_wait_all()
+{
+#ifndef HUF_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
 template <typename T>

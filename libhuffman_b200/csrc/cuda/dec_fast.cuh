@@ -44,22 +44,22 @@ constexpr int kLongMax = 256;
 constexpr int kLongBits = 32;             // longest code word the fast lane handles
 constexpr int kTreeReach = kLutBits + 1;  // code bits resolved by the table incl. the root bit
 
-// Fast-lane table entries (u16): leaf = length << 8 | symbol (length 1..13); the two special
-// kinds carry a length field of 1 so that a walk which only needs to make progress (warm-up)
-// can add bits [11:8] blindly.
-constexpr uint32_t kFastDead = kLutDead | 0x100;  // walks into an absent child
-constexpr uint32_t kFastLong = kLutLong | 0x100;  // code word longer than the table reach
-constexpr uint32_t kFastFlags = 0xc000u;
+// Fast-lane table entries (u16): leaf = symbol << 8 | length (1..13); the two special kinds
+// carry a length field of 1 so that a walk which only needs to make progress (warm-up) can
+// add bits [3:0] blindly.
+constexpr uint32_t kFastDead = 0x41;   // walks into an absent child
+constexpr uint32_t kFastLong = 0x81;   // code word longer than the table reach
+constexpr uint32_t kFastFlags = 0xc0u;
 
 // two meta words per candidate: [0] bit 0 = eligible for the fast lane, [15:8] shortest code
 // length, [31:16] number of terminals; [1] number of long-code records
 constexpr uint32_t kMetaFast = 1u;
 
-constexpr int kFT = 256;                  // threads per CTA
-constexpr int kRegStride = 252;           // bytes per thread region (63 words: conflict-free)
+constexpr int kFT = 512;                  // threads per CTA
+constexpr int kRegStride = 124;           // bytes per thread region (31 words: conflict-free)
 constexpr int kRegPad = 12;               // room in front of the speculative symbols
-constexpr int kRegCap = 240;              // symbols a region can hold behind the pad
-constexpr int kMaxSubWords = 29;          // payload words per thread per chunk (odd)
+constexpr int kRegCap = 112;              // symbols a region can hold behind the pad
+constexpr int kMaxSubWords = 15;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
@@ -84,78 +84,86 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
 
     for (uint64_t g0 = (uint64_t)blockIdx.x * 32; g0 < ncand; g0 += (uint64_t)gridDim.x * 32) {
         __syncwarp();
-        // ---- stage the 32 headers: whole aligned words, copied verbatim
-        uint32_t my_tl = 0, my_skew = 0;
-        uint64_t my_ol = 0;
+        // ---- every lane reads the fixed header fields of its own candidate ...
+        uint64_t my_off = 0, my_ol = 0;
+        uint32_t my_tl = 0;
         bool my_ok = false;
+        {
+            const uint64_t j = g0 + lane;
+            bool ok = in_ok && j < ncand && j < a.term_slots;
+            if (ok) {
+                my_off = a.cand[j];
+                ok = my_off + kHdrFixed + 4 <= a.avail;
+            }
+            if (ok) {
+                my_ol = rd_u64(a.in + my_off);
+                my_tl = rd_u16(a.in + my_off + 8);
+                ok = my_ol != 0 && my_tl >= 5 && my_tl <= (a.accept_1025 ? 1025u : 1024u) &&
+                     my_off + kHdrFixed + 2ull * my_tl <= a.avail;
+            }
+            my_ok = ok;
+        }
+        // ... then the warp stages the 32 serialised trees: whole aligned words copied verbatim,
+        // asynchronously, all in flight together
         for (int c = 0; c < 32; c++) {
-            const uint64_t j = g0 + c;
-            if (j >= ncand) break;
-            bool ok = in_ok && j < a.term_slots;
-            uint64_t off = 0, ol = 0;
-            uint32_t tl = 0;
-            if (ok) {
-                off = a.cand[j];
-                ok = off + kHdrFixed + 4 <= a.avail;
-            }
-            if (ok) {
-                ol = rd_u64(a.in + off);
-                tl = rd_u16(a.in + off + 8);
-                ok = ol != 0 && tl >= 5 && tl <= (a.accept_1025 ? 1025u : 1024u) &&
-                     off + kHdrFixed + 2ull * tl <= a.avail;
-            }
-            if (ok) {
-                const uint64_t b0 = off + kHdrFixed;
-                const uint64_t w0 = b0 >> 2, w1 = (b0 + 2ull * tl + 3) >> 2;  // word range
-                uint32_t *dst = reinterpret_cast<uint32_t *>(hdr + c * kTreeHdrStride);
-                for (uint64_t k = w0 + lane; k < w1; k += 32) {
+            if (!__shfl_sync(kFull, (int)my_ok, c)) continue;
+            const uint64_t b0 = __shfl_sync(kFull, my_off, c) + kHdrFixed;
+            const uint32_t tl = __shfl_sync(kFull, my_tl, c);
+            const uint64_t w0 = b0 >> 2, w1 = (b0 + 2ull * tl + 3) >> 2;  // word range
+            uint32_t *dst = reinterpret_cast<uint32_t *>(hdr + c * kTreeHdrStride);
+            for (uint64_t k = w0 + lane; k < w1; k += 32) {
+                if (4 * k + 4 <= a.avail) {
+                    cp_async4(dst + (k - w0), reinterpret_cast<const uint32_t *>(a.in) + k);
+                } else {
                     uint32_t v = 0;
-                    if (4 * k + 4 <= a.avail) {
-                        v = reinterpret_cast<const uint32_t *>(a.in)[k];
-                    } else {
-                        for (int q = 0; q < 4; q++) {
-                            if (4 * k + q < a.avail) v |= (uint32_t)a.in[4 * k + q] << (8 * q);
-                        }
+                    for (int q = 0; q < 4; q++) {
+                        if (4 * k + q < a.avail) v |= (uint32_t)a.in[4 * k + q] << (8 * q);
                     }
                     dst[k - w0] = v;
                 }
-                if (c == lane) {
-                    my_skew = (uint32_t)(b0 & 3);
-                    my_tl = tl;
-                    my_ol = ol;
-                }
             }
-            if (c == lane) my_ok = ok;
         }
+        cp_async_wait_all();
         __syncwarp();
+        const uint32_t my_skew = (uint32_t)((my_off + kHdrFixed) & 3);
 
         // ---- every lane walks its own tree
         const uint64_t j = g0 + lane;
         uint32_t meta = 0, nlong = 0;
         if (j < ncand && my_ok && my_ol) {
-            const uint8_t *el = hdr + lane * kTreeHdrStride + my_skew;
+            const uint32_t *hw = reinterpret_cast<const uint32_t *>(hdr + lane * kTreeHdrStride);
             const uint32_t tl = my_tl;
-            // elements past tree_len read as absent children (src/tree.c:154-160)
-            auto elem = [&](uint32_t i) -> int {
-                return i < tl ? (int)(int16_t)(el[2 * i] | ((uint32_t)el[2 * i + 1] << 8)) : -1;
+            // Elements i, i+1, i+2 (sign-extended; past tree_len they read as absent children,
+            // src/tree.c:154-160).  The staged words keep the stream's byte skew: three words
+            // and two funnel shifts deliver four consecutive elements.
+            auto elems3 = [&](uint32_t i, int &x0, int &x1, int &x2) {
+                const uint32_t byte = my_skew + 2 * i;
+                const uint32_t w = byte >> 2, sh = (byte & 3) * 8;
+                const uint32_t a0 = hw[w], a1 = hw[w + 1], a2 = hw[w + 2];
+                const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                x0 = i < tl ? (int)(int16_t)(lo & 0xffffu) : -1;
+                x1 = i + 1 < tl ? (int)(int16_t)(lo >> 16) : -1;
+                x2 = i + 2 < tl ? (int)(int16_t)(hi & 0xffffu) : -1;
             };
             uint32_t *slot = a.terms + j * kTermStride;
-            uint32_t stk[kLongBits + 8];  // ancestors whose right slot is pending: element | depth << 16
-            int sp = 0;
-            stk[sp++] = 0;                // the root, depth 0
+            // Ancestors whose right slot is still open, one bit per depth: every node opens its
+            // right slot exactly once, so the pending stack is a bit mask and a pop is a clz.
+            uint64_t pend = 1;            // the root, depth 0
             uint32_t i = 1, D = 1;        // slot being filled: depth D ...
             uint64_t C = 0;               // ... reached by the path bits C
             uint32_t nterm = 0, min_len = kTreeReach + 1;
-            bool ok = elem(0) != -1 && elem(1) != -1;  // a root with something below its left edge
+            int e, e1, e2;
+            elems3(0, e, e1, e2);
+            bool ok = e != -1 && e1 != -1;  // a root with something below its left edge
             while (ok) {
-                const int e = elem(i);
+                elems3(i, e, e1, e2);
                 bool pop;
                 if (e != -1) {
-                    if (elem(i + 1) == -1 && elem(i + 2) == -1) {  // leaf: v, absent, absent
-                        const uint32_t entry = (D << 8) | (uint32_t)(e & 0xff);
+                    if (e1 == -1 && e2 == -1) {  // leaf: v, absent, absent
                         if (D <= (uint32_t)kTreeReach) {
                             if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                            slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) | entry;
+                            slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) |
+                                            ((uint32_t)(e & 0xff) << 8) | D;
                             min_len = min(min_len, D);
                         } else {
                             if (nlong >= (uint32_t)kLongMax || nterm + 2 * nlong + 3 > (uint32_t)kTermStride) {
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
                                 break;
                             }
                             slot[kTermStride - 2 * (nlong + 1)] = (uint32_t)(C << (kLongBits - D));
-                            slot[kTermStride - 2 * (nlong + 1) + 1] = entry;
+                            slot[kTermStride - 2 * (nlong + 1) + 1] = (D << 8) | (uint32_t)(e & 0xff);
                             nlong++;
                         }
                         i += 3;
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
                             if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
                             slot[nterm++] = ((uint32_t)C << 16) | kFastLong;
                         }
-                        stk[sp++] = i | (D << 16);
+                        pend |= 1ull << D;
                         i++;
                         D++;
                         C <<= 1;
@@ -194,13 +202,16 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
                     pop = true;
                 }
                 if (pop) {
-                    if (sp == 0) break;  // every slot filled: the tree is complete
-                    const uint32_t s = stk[--sp];
-                    const uint32_t d = s >> 16;
+                    if (pend == 0) break;  // every slot filled: the tree is complete
+                    const uint32_t d = 63u - (uint32_t)__clzll((long long)pend);  // deepest open right slot
+                    pend &= ~(1ull << d);
                     C = ((C >> (D - d)) << 1) | 1u;
                     D = d + 1;
                     // the right slot of the root must stay empty (table sits behind the root bit)
-                    if (d == 0 && elem(i) != -1) ok = false;
+                    if (d == 0) {
+                        elems3(i, e, e1, e2);
+                        if (e != -1) ok = false;
+                    }
                 }
             }
             if (ok) meta = kMetaFast | (min_len << 8) | (nterm << 16);
@@ -239,64 +250,79 @@ __device__ __forceinline__ uint32_t fast_look(const uint32_t *sw, const uint16_t
 
 // Four consecutive table entries from `pos` on: three staged words are loaded once into a
 // 64-bit left-aligned bit buffer that is shifted by every code length (4 x 13 bits fit).
-// Positions advance by bits [11:8] of each entry.  Returns the position behind the fourth.
+// Positions advance by bits [3:0] of each entry.  Returns the position behind the fourth.
 __device__ __forceinline__ uint32_t fast_look4(const uint32_t *sw, const uint16_t *lut, uint32_t pos,
-                                               uint32_t &e0, uint32_t &e1, uint32_t &e2, uint32_t &e3)
+                                               uint32_t &e0, uint32_t &e1, uint32_t &e2, uint32_t &e3,
+                                               uint32_t &last_start)
 {
     const uint32_t wi = pos >> 5;
     const uint32_t w0 = sw[wi], w1 = sw[wi + 1], w2 = sw[wi + 2];
     uint32_t hi = __funnelshift_l(w1, w0, pos);  // stream bits pos .. pos+31
     uint32_t lo = __funnelshift_l(w2, w1, pos);  // stream bits pos+32 .. pos+63
     e0 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l0 = (e0 >> 8) & 0xfu;
+    const uint32_t l0 = e0 & 0xfu;
     hi = __funnelshift_l(lo, hi, l0);
     lo <<= l0;
     e1 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l1 = (e1 >> 8) & 0xfu;
+    const uint32_t l1 = e1 & 0xfu;
     hi = __funnelshift_l(lo, hi, l1);
     lo <<= l1;
     e2 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l2 = (e2 >> 8) & 0xfu;
+    const uint32_t l2 = e2 & 0xfu;
     hi = __funnelshift_l(lo, hi, l2);
     e3 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l3 = (e3 >> 8) & 0xfu;
-    return pos + l0 + l1 + l2 + l3;
+    const uint32_t l3 = e3 & 0xfu;
+    last_start = pos + l0 + l1 + l2;  // where the fourth code word starts
+    return last_start + l3;
 }
 
 // One exact decode step at staged bit position `pos`: true + symbol when a code word starts
 // there (table hit or long-code record), false when the walk dies (pos advances one bit: any
 // deterministic rule serves a speculative start, and a dead step on the proven trajectory sends
 // the block to the general lane).
-__device__ __forceinline__ bool fast_step(const uint32_t *sw, const FastSmem &sm, uint32_t &pos,
-                                          uint32_t &sym)
+__device__ __noinline__ bool fast_step(const uint32_t *sw, const FastSmem &sm, uint32_t &pos,
+                                       uint32_t &sym)
 {
     const uint32_t wi = pos >> 5;
     const uint32_t win = __funnelshift_l(sw[wi + 1], sw[wi], pos);
     const uint32_t e = sm.lut[min(win >> (32 - kTreeReach), (uint32_t)kLutSize)];
     if (!(e & kFastFlags)) {
-        sym = e & 0xffu;
-        pos += e >> 8;
+        sym = e >> 8;
+        pos += e & 0xffu;
         return true;
     }
-    if (e & kLutLong) {
-        // last record with code <= window; prefix-free codes: it is the only possible match
-        uint32_t lo = 0, hi = sm.nlong;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (sm.long_code[mid] <= win) lo = mid; else hi = mid;
+    if ((e & 0x80u) && sm.nlong) {
+        // last record with code <= window (prefix-free codes: the only possible match), found
+        // with a fixed number of halving steps
+        const uint32_t n = sm.nlong;
+        uint32_t lo = 0;
+#pragma unroll
+        for (uint32_t step = kLongMax / 2; step; step >>= 1) {
+            const uint32_t mid = lo + step;
+            if (mid < n && sm.long_code[mid] <= win) lo = mid;
         }
-        if (hi) {
-            const uint32_t ent = sm.long_ent[lo];
-            const uint32_t len = ent >> 8;
-            if (((win ^ sm.long_code[lo]) >> (32 - len)) == 0) {
-                sym = ent & 0xffu;
-                pos += len;
-                return true;
-            }
+        const uint32_t ent = sm.long_ent[lo];
+        const uint32_t len = ent >> 8;
+        if (((win ^ sm.long_code[lo]) >> (32 - len)) == 0) {
+            sym = ent & 0xffu;
+            pos += len;
+            return true;
         }
     }
     pos += 1;
     return false;
+}
+
+// CTA barrier behind divergent per-thread loops: the warp is explicitly reconverged first
+// (the aligned barrier instruction requires all 32 lanes to arrive together).
+__device__ __forceinline__ void cta_sync()
+{
+#ifndef HUF_EMU
+    asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+#else
+    __syncwarp();
+#endif
+    __syncthreads();
 }
 
 // Copy n bytes between two shared-memory locations of arbitrary alignment, word-wise.
@@ -341,7 +367,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
     const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
     for (uint64_t j = blockIdx.x; j < ncand; j += gridDim.x) {
-        __syncthreads();
+        cta_sync();
         const uint32_t meta = a.meta[2 * j];
         const uint32_t nlong = a.meta[2 * j + 1];
         const uint64_t off = a.cand[j];
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 sm.redo = 0;
                 sm.nlong = nlong;
             }
-            __syncthreads();
+            cta_sync();
             constexpr int kPer = kLutSize / kFT;  // 16
             const uint32_t idx0 = (uint32_t)tid * kPer;
             uint32_t lo = 0, hi = nterm;  // last terminal with start <= idx0 (terminal 0 starts at 0)
@@ -405,7 +431,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             }
         }
-        __syncthreads();
+        cta_sync();
 
         // ---- chunk loop
         const uint64_t next_cand = (j + 1 < ncand) ? a.cand[j + 1] : a.avail;
@@ -418,7 +444,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
         const uint64_t out0 = a.out_off[j];
         const bool can_write = !a.count_only && out0 + orig_len <= a.out_cap;
         uint32_t sub_cap_w = min((uint32_t)kMaxSubWords, (kRegCap * min_len) / 32u);
-        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 7, so never below 7
+        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 3, so never below 3
         // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
         uint32_t warm = 160;
         if (use_guess) {
@@ -440,17 +466,23 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             const uint64_t base16 = (next_bit >> 3) & ~uint64_t(15);
             const uint32_t rel_start = (uint32_t)(next_bit - 8ull * base16);
             const uint32_t A = rel_start & ~31u;
-            const uint64_t span = limit - (8ull * base16 + A);
-            const uint64_t chunk_cap = (uint64_t)kFT * 32u * sub_cap_w;
-            const uint64_t nch = (span + chunk_cap - 1) / chunk_cap;
-            uint32_t subw = (uint32_t)((span + nch * kFT * 32u - 1) / (nch * kFT * 32u));
+            // split what is left evenly over as few chunks as possible (32-bit arithmetic: a
+            // span beyond 4 Gbit only needs the right order of magnitude)
+            const uint64_t span64 = limit - (8ull * base16 + A);
+            const uint32_t span = span64 > 0xf0000000ull ? 0xf0000000u : (uint32_t)span64;
+            const uint32_t chunk_cap = (uint32_t)kFT * 32u * sub_cap_w;
+            const uint32_t nch = (span + chunk_cap - 1) / chunk_cap;
+            const uint32_t per_word = nch * (uint32_t)kFT * 32u;
+            uint32_t subw = (span + per_word - 1) / per_word;
             subw |= 1u;
-            if (subw < 7) subw = 7;
+            if (subw < 3) subw = 3;
             if (subw > sub_cap_w) subw = sub_cap_w;
             const uint32_t sub = subw * 32u;
             const uint64_t lim_rel = limit - 8ull * base16;
             const uint64_t cov64 = (uint64_t)A + (uint64_t)kFT * sub;
             const uint32_t cover = (uint32_t)(cov64 < lim_rel ? cov64 : lim_rel);
+            // threads whose sub-block starts inside the covered bits take part in this chunk
+            const uint32_t nact = (cover - A + sub - 1) / sub;
 
             // (0) stage the chunk: 16-byte loads, bytes past `avail` read as zero
             {
@@ -471,7 +503,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                         make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
                 }
             }
-            __syncthreads();
+            cta_sync();
 
             // (1) warm-up in front of my sub-block, then decode it into my region
             const uint32_t my_lo = tid == 0 ? rel_start : min(A + (uint32_t)tid * sub, cover);
@@ -480,43 +512,67 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             if (tid > 0 && my_lo < my_hi) {
                 // start `warm` bits early (or at the proven chunk start when that is closer)
                 pos = my_lo > rel_start + warm ? my_lo - warm : rel_start;
-                uint32_t e0, e1, e2, e3;
-                while (pos + 4 * kTreeReach <= my_lo) pos = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3);
-                while (pos < my_lo) pos += (fast_look(sw, sm.lut, pos) >> 8) & 0xfu;
+                // four steps at a time while all four start in front of my sub-block
+                while (pos < my_lo) {
+                    uint32_t e0, e1, e2, e3, p3;
+                    const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
+                    if (p3 >= my_lo) {
+                        // the fourth starts behind the boundary: take the steps in front of it
+                        if (pos < my_lo) pos += e0 & 0xfu;
+                        if (pos < my_lo) pos += e1 & 0xfu;
+                        if (pos < my_lo) pos += e2 & 0xfu;
+                        break;
+                    }
+                    pos = np;
+                }
             }
             uint32_t start = pos;  // first code word of mine (speculative unless tid == 0)
-            if (pos < my_hi) {
-                for (;;) {
-                    while (pos + 4 * kTreeReach <= my_hi && !(cnt & 3)) {
-                        uint32_t e0, e1, e2, e3;
-                        const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3);
-                        if ((e0 | e1 | e2 | e3) & kFastFlags) break;
+            while (pos < my_hi) {
+                uint32_t e0, e1, e2, e3, p3;
+                const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
+                if (!((e0 | e1 | e2 | e3) & kFastFlags) && !(cnt & 3)) {
+                    // four plain table hits
+                    if (p3 < my_hi) {
+                        // ... that all start inside my sub-block: one 32-bit store
                         pos = np;
-                        const uint32_t lo2 = __byte_perm(e0, e1, 0x0040);
-                        const uint32_t hi2 = __byte_perm(e2, e3, 0x0040);
+                        const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
+                        const uint32_t hi2 = __byte_perm(e2, e3, 0x0051);
                         *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = __byte_perm(lo2, hi2, 0x5410);
                         cnt += 4;
+                        continue;
                     }
-                    if (pos >= my_hi) break;
-                    const uint32_t at = pos;
-                    uint32_t sy;
-                    if (fast_step(sw, sm, pos, sy)) {
-                        reg[kRegPad + cnt] = (uint8_t)sy;
-                        cnt++;
-                    } else {
-                        last_dead = at;
+                    // the fourth starts behind the boundary: at most three are mine
+                    reg[kRegPad + cnt++] = (uint8_t)(e0 >> 8);
+                    pos += e0 & 0xfu;
+                    if (pos < my_hi) {
+                        reg[kRegPad + cnt++] = (uint8_t)(e1 >> 8);
+                        pos += e1 & 0xfu;
                     }
+                    if (pos < my_hi) {
+                        reg[kRegPad + cnt++] = (uint8_t)(e2 >> 8);
+                        pos += e2 & 0xfu;
+                    }
+                    break;
+                }
+                // irregular (special entry among the four, or an unaligned count): one exact step
+                const uint32_t at = pos;
+                uint32_t sy;
+                if (fast_step(sw, sm, pos, sy)) {
+                    reg[kRegPad + cnt] = (uint8_t)sy;
+                    cnt++;
+                } else {
+                    last_dead = at;
                 }
             }
             uint32_t end = pos;
             sm.sub_end[tid] = end;
-            __syncthreads();
+            cta_sync();
 
             // (2) verification and (rare) sync-point fix-up
             for (int round = 0; round < kFT; round++) {
-                const uint32_t want = tid == 0 ? start : sm.sub_end[tid - 1];
+                const uint32_t want = (tid == 0 || (uint32_t)tid >= nact) ? start : sm.sub_end[tid - 1];
                 const bool redo = want != start;
-                __syncthreads();
+                cta_sync();
                 if (redo) {
                     if (want >= my_hi) {
                         cnt = 0;
@@ -568,6 +624,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     start = want;
                     sm.sub_end[tid] = end;
                 }
+                __syncwarp();
                 if (!__syncthreads_or(redo)) break;
             }
 
@@ -575,14 +632,14 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             const uint32_t incl = warp_incl_scan(cnt);
             if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
             if (tid == 0) sm.fin_found = 0;
-            __syncthreads();
+            cta_sync();
             if (tid < 32) {
                 const uint32_t t = tid < kFT / 32 ? sm.warp_tot[tid] : 0;
                 const uint32_t ti = warp_incl_scan(t);
                 if (tid < kFT / 32) sm.warp_tot[tid] = ti - t;
                 if (tid == kFT / 32 - 1) sm.total = ti;
             }
-            __syncthreads();
+            cta_sync();
             const uint32_t before = sm.warp_tot[tid >> 5] + incl - cnt;
             const uint32_t total = sm.total;
             const uint64_t remaining = orig_len - produced;
@@ -601,7 +658,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 sm.fin_end = p;
                 sm.fin_found = 1;
             }
-            __syncthreads();
+            cta_sync();
             if (sm.redo) {
                 status = kRedo;
                 break;
@@ -620,7 +677,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     const uint32_t we = wb + kFastOutWin;
                     const uint32_t c0 = max(y0, wb), c1 = min(y1, we);
                     if (c0 < c1) smem_copy(obuf + (c0 - wb), reg + roff + (c0 - y0), c1 - c0);
-                    __syncthreads();
+                    cta_sync();
                     const uint32_t vend = min(yend, we) - wb;          // valid bytes end (window relative)
                     const uint32_t vbeg = wb == 0 ? m : 0;             // valid bytes begin
                     uint8_t *gbase = dst0 - m + wb;                    // 16-byte aligned
@@ -633,7 +690,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                             for (uint32_t q = max(b0, vbeg); q < min(b1, vend); q++) gbase[q] = obuf[q];
                         }
                     }
-                    __syncthreads();
+                    cta_sync();
                 }
             }
             produced += total_copy;
@@ -641,8 +698,8 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 end_bit = 8ull * base16 + sm.fin_end;
                 break;
             }
-            next_bit = 8ull * base16 + sm.sub_end[kFT - 1];
-            __syncthreads();
+            next_bit = 8ull * base16 + sm.sub_end[nact - 1];
+            cta_sync();
         }
 
         if (status == kOk && end_bit > room_end) status = kRedo;  // last code word leaves the readable bytes

@@ -29,6 +29,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
 #define __align__(x) alignas(x)
@@ -306,6 +307,8 @@ inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s)
     }
     return r;
 }
+inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31));

@@ -253,3 +253,25 @@ def test_encode_is_idempotent_and_block_local(lib, torch_cuda, codec):
     second, _ = dev_encode(torch, codec, x[32 << 20:], bs)
     assert torch.equal(torch.cat([first, second]), whole)
     assert first.numel() == int(offs[half])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [4096, 65536, 1 << 20])
+@pytest.mark.parametrize("shape", ["english", "zipf255", "fibonacci", "geometric"])
+def test_shape_blocksize_matrix(lib, harness, shape, bs):
+    """Every named shape at small, headline and large blocks: long code words (English text at
+    4 KiB blocks reaches 14 bits, Fibonacci counts 22-28 bits), many chunks per block, blocks
+    smaller than one chunk.  8 MiB of Fibonacci data at 64 KiB blocks once exposed a divergent
+    barrier in the fast decode lane, hence the size."""
+    n = 8 << 20
+    data = {
+        "english": lambda: datagen.english_text(n, seed=1),
+        "zipf255": lambda: datagen.zipf(n, 255, seed=2),
+        "fibonacci": lambda: datagen.fibonacci(n, 65536, seed=4),
+        "geometric": lambda: datagen.geometric(n, seed=4),
+    }[shape]()
+    want = harness.oracle_encode(data, bs)
+    rc, got = lib.encode(data, bs)
+    assert rc == 0 and got == want
+    rc, back = lib.decode(want)
+    assert rc == 0 and back == data
