@@ -1,0 +1,312 @@
+// enc_build.cuh — K2 of the encode path split in three kernels (blocks of at most 4 MiB; larger
+// blocks keep the fused k_build<uint64_t> of enc_kernels.cuh):
+//
+//   K2a k_build_sort   one WARP per block: block histogram = sum of its segment histograms,
+//                      keys (weight << 9 | 511 - symbol) sorted ascending -> blk_keys.
+//   K2b k_build_merge  one LANE per block: the min-pair merge of huf_tree_from_histogram
+//                      (reference src/tree.c:292-427) is a strictly serial chain of up to 256
+//                      steps, so 32 blocks advance in lockstep per warp with every per-block
+//                      array transposed in shared memory ([index][lane]: conflict-free whatever
+//                      index a lane touches).  Exact tie-break: two-queue merge in which equal
+//                      weight runs of merge nodes are consumed newest first and a merge node
+//                      beats a leaf of equal weight (later index wins, src/tree.c:341,347).
+//                      Emits {left, right, leaves below} per merge node -> blk_nodes.
+//   K2c k_build_codes  one WARP per block: parents, code words and pre-order positions by
+//                      climbing to the root (__huf_create_char_coding, src/encoder.c:40-81;
+//                      huf_tree_serialize, src/tree.c:233-289), code table, segment bit
+//                      offsets, block size.
+#pragma once
+
+#include "enc_kernels.cuh"
+
+namespace hufb200 {
+
+constexpr int kMergeDyn = 256 * 32 * 4;  // one u32 per merge node and lane
+
+// ------------------------------------------------------------------------------------------
+// K2a
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kBuildWarps * 32) k_build_sort(EncArgs a)
+{
+    __shared__ uint32_t key_all[kBuildWarps][256];
+    const int lane = lane_id();
+    const uint64_t bl = (uint64_t)blockIdx.x * kBuildWarps + warp_in_cta();  // pass-local block
+    if (bl >= a.npass) return;
+    const uint64_t b = a.blk0 + bl;
+    uint32_t *key = key_all[warp_in_cta()];
+    const uint32_t kMax = ~0u;
+
+    const uint64_t blen = blk_len_of(a, b);
+    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
+    const uint64_t g0 = bl * a.nspb;
+
+    // block histogram: lane owns symbols 8*lane .. 8*lane+7
+    uint32_t cnt[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cnt[i] = 0;
+    for (uint32_t k = 0; k < nseg_b; k++) {
+        uint4 v = reinterpret_cast<const uint4 *>(a.seg_hist + (g0 + k) * 256)[lane];
+        cnt[0] += v.x & 0xffffu; cnt[1] += v.x >> 16;
+        cnt[2] += v.y & 0xffffu; cnt[3] += v.y >> 16;
+        cnt[4] += v.z & 0xffffu; cnt[5] += v.z >> 16;
+        cnt[6] += v.w & 0xffffu; cnt[7] += v.w >> 16;
+    }
+    uint32_t present = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t s = lane * 8 + i;
+        key[s] = cnt[i] ? make_key<uint32_t>(cnt[i], s) : kMax;
+        present += cnt[i] != 0;
+    }
+    const uint32_t n = warp_sum(present);  // distinct symbols, >= 1
+    __syncwarp();
+
+    // bitonic sort of the 256 keys (absent symbols sort to the end)
+    for (uint32_t k = 2; k <= 256; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (uint32_t t = lane; t < 128; t += 32) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t p = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t x = key[i], y = key[p];
+                if ((x > y) == up) {
+                    key[i] = y;
+                    key[p] = x;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    uint32_t *dst = a.blk_keys + bl * 256;
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[lane + 32 * i] = key[lane + 32 * i];
+    if (lane == 0) a.blk_meta[bl * 4 + 3] = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
+{
+#ifdef HUF_EMU
+    uint32_t *nodev = reinterpret_cast<uint32_t *>(hufemu::dyn_smem());
+#else
+    extern __shared__ __align__(16) uint32_t nodev[];
+#endif
+    // nodev[j * 32 + lane] = weight << 8 | (leaves below - 1) of merge node 256 + j
+    const int lane = lane_id();
+    const uint64_t bl = (uint64_t)blockIdx.x * 32 + lane;  // pass-local block
+    if (bl >= a.npass) return;
+    const uint32_t kMax = ~0u;
+    const uint32_t n = a.blk_meta[bl * 4 + 3];
+    const uint32_t *keys = a.blk_keys + bl * 256;  // ascending, n real keys
+    uint2 *out = reinterpret_cast<uint2 *>(a.blk_nodes) + bl * 256;
+    uint32_t *mine = nodev + lane;
+#define NODEV(j) mine[(j) * 32]
+
+    // Leaves are consumed in key order (two keys prefetched).  Merge nodes are created with
+    // non-decreasing weight, so they form runs of equal weight in creation order; the live
+    // ones are [head, top) -- the front run, consumed newest first, its weight in `runw` --
+    // plus [nxt, made).
+    uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0;
+    uint32_t runw = 0;
+    uint32_t k0 = keys[0];  // n >= 1
+    uint32_t k1 = n > 1 ? keys[1] : kMax;
+    for (;;) {
+        uint32_t pick0 = 0, pick1 = kNone16;
+        uint32_t w0 = 0, w1 = 0, nl = 0;
+        int got = 0;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (top == head && nxt < made) {  // front run used up: open the next one
+                head = nxt;
+                runw = NODEV(nxt) >> 8;
+                uint32_t e = nxt + 1;
+                while (e < made && (NODEV(e) >> 8) == runw) e++;
+                top = nxt = e;
+            }
+            const bool has_i = top > head;
+            const uint32_t ikey = has_i ? make_key<uint32_t>(runw, 255u + top) : kMax;
+            if (ikey == kMax && k0 == kMax) break;  // nothing left (second pick only)
+            uint32_t pick, pw, pl;
+            if (ikey < k0) {
+                top--;
+                pick = 256u + top;
+                pw = runw;
+                pl = (NODEV(top) & 0xffu) + 1u;
+                if (top == head) head = top = nxt;
+            } else {
+                pick = 511u - (k0 & 511u);
+                pw = k0 >> 9;
+                pl = 1;
+                li++;
+                k0 = k1;
+                k1 = li + 1 < n ? keys[li + 1] : kMax;
+            }
+            if (s == 0) {
+                pick0 = pick;
+                w0 = pw;
+            } else {
+                pick1 = pick;
+                w1 = pw;
+            }
+            nl += pl;
+            got++;
+        }
+        const uint32_t weight = w0 + (got == 2 ? w1 : 0u);
+        NODEV(made) = (weight << 8) | (nl - 1u);
+        out[made] = make_uint2(pick0 | (pick1 << 16), nl);
+        // an open front run that is still untouched and is the newest run grows with it
+        if (top > head && top == nxt && nxt == made && weight == runw) {
+            top++;
+            nxt++;
+        }
+        made++;
+        if (got < 2) break;
+    }
+#undef NODEV
+}
+
+// ------------------------------------------------------------------------------------------
+// K2c
+// ------------------------------------------------------------------------------------------
+
+struct CodesSmem {
+    uint16_t isz[256];   // serialised size (elements) of the subtree of merge node 256 + j
+    uint16_t lch[256];
+    uint16_t rch[256];
+    uint16_t par[512];
+    uint8_t len[256];
+};
+
+__global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(EncArgs a)
+{
+    __shared__ CodesSmem sm_all[kBuildWarps];
+    const int lane = lane_id();
+    const uint64_t bl = (uint64_t)blockIdx.x * kBuildWarps + warp_in_cta();
+    if (bl >= a.npass) return;
+    const uint64_t b = a.blk0 + bl;
+    CodesSmem &sm = sm_all[warp_in_cta()];
+    const uint64_t blen = blk_len_of(a, b);
+    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
+    const uint64_t g0 = bl * a.nspb;
+    const uint32_t n = a.blk_meta[bl * 4 + 3];  // distinct symbols = merge nodes made
+
+    for (int i = lane; i < 512; i += 32) sm.par[i] = kNone16;
+    for (int i = lane; i < 256; i += 32) sm.len[i] = 0;
+    __syncwarp();
+    const uint2 *nodes = reinterpret_cast<const uint2 *>(a.blk_nodes) + bl * 256;
+    for (uint32_t j = lane; j < n; j += 32) {
+        const uint2 v = nodes[j];
+        const uint32_t l = v.x & 0xffffu, r = v.x >> 16;
+        sm.lch[j] = (uint16_t)l;
+        sm.rch[j] = (uint16_t)r;
+        // a subtree with L leaves below a two-child node serialises to 4L - 1 elements; the
+        // one-child root adds itself and its absent right child
+        sm.isz[j] = (uint16_t)(r == kNone16 ? 4 * v.y + 1 : 4 * v.y - 1);
+        sm.par[l] = (uint16_t)(256u + j);
+        if (r != kNone16) sm.par[r] = (uint16_t)(256u + j);
+    }
+    __syncwarp();
+
+    // climb from every node to the root: code word + pre-order position
+    const uint32_t root = 255u + n;
+    const uint32_t tree_len = sm.isz[n - 1];
+    int16_t *tree = a.blk_tree + bl * kTreeStride;
+    uint32_t *tab32 = a.blk_table + bl * 512;
+    uint32_t my_max = 0;
+    uint64_t code_of[8];
+    uint32_t len_of[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t s = lane + 32 * i;
+        uint64_t code = 0;
+        uint32_t len = 0, pos = 0;
+        if (sm.par[s] != kNone16) {
+            uint32_t x = s;
+            while (x != root) {
+                const uint32_t p = sm.par[x];
+                const uint32_t pj = p - 256u;
+                if (sm.rch[pj] == x) {
+                    const uint32_t l = sm.lch[pj];
+                    code |= 1ull << len;
+                    pos += l < 256u ? 3u : sm.isz[l - 256u];
+                }
+                pos += 1;
+                len++;
+                x = p;
+            }
+            tree[pos] = (int16_t)s;
+            tree[pos + 1] = -1;
+            tree[pos + 2] = -1;
+            sm.len[s] = (uint8_t)len;
+        }
+        code_of[i] = code;
+        len_of[i] = len;
+        my_max = max(my_max, len);
+    }
+    for (uint32_t v = 256u + lane; v <= root; v += 32) {
+        uint32_t pos = 0, x = v;
+        while (x != root) {
+            const uint32_t p = sm.par[x];
+            const uint32_t pj = p - 256u;
+            if (sm.rch[pj] == x) {
+                const uint32_t l = sm.lch[pj];
+                pos += l < 256u ? 3u : sm.isz[l - 256u];
+            }
+            pos += 1;
+            x = p;
+        }
+        tree[pos] = (int16_t)v;
+    }
+    if (lane == 0) tree[tree_len - 1] = -1;  // absent right child of the one-child root
+
+    const uint32_t max_len = warp_max(my_max);
+    const uint32_t fmt = max_len <= 26 ? 0u : 1u;
+    if (max_len > 56 && lane == 0) {
+        atomicMax(&a.status[0], (uint32_t)kErrFatal);
+        a.status[1] = max_len;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t s = lane + 32 * i;
+        const uint32_t len = len_of[i];
+        if (fmt == 0) {
+            tab32[s] = len ? ((uint32_t)code_of[i] << (32 - len)) | len : 0u;
+        } else {
+            const uint64_t e = len ? (code_of[i] << (64 - len)) | len : 0ull;
+            reinterpret_cast<uint64_t *>(tab32)[s] = e;
+        }
+    }
+    __syncwarp();
+
+    // payload bit offset of every segment = running dot(segment histogram, code length)
+    uint32_t l8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) l8[i] = sm.len[lane * 8 + i];
+    uint64_t run = 0;
+    for (uint32_t k = 0; k < nseg_b; k++) {
+        uint4 v = reinterpret_cast<const uint4 *>(a.seg_hist + (g0 + k) * 256)[lane];
+        uint32_t d = (v.x & 0xffffu) * l8[0] + (v.x >> 16) * l8[1] +
+                     (v.y & 0xffffu) * l8[2] + (v.y >> 16) * l8[3] +
+                     (v.z & 0xffffu) * l8[4] + (v.z >> 16) * l8[5] +
+                     (v.w & 0xffffu) * l8[6] + (v.w >> 16) * l8[7];
+        d = warp_sum(d);
+        if (lane == 0) a.seg_bitoff[g0 + k] = run;
+        run += d;
+    }
+    if (lane == 0) {
+        a.blk_bits[bl] = run;
+        a.blk_size[b] = (uint64_t)kHdrFixed + 2ull * tree_len + ((run + 7) >> 3);
+        uint32_t *m = a.blk_meta + bl * 4;
+        m[0] = tree_len;
+        m[1] = max_len;
+        m[2] = fmt;
+        m[3] = n;
+    }
+}
+
+}  // namespace hufb200

@@ -27,6 +27,8 @@
 //                                         fmt1: 256 x u64 (code<<(64-len) | len), len <= 56
 //   blk_tree   i16 [nblocks][kTreeStride] pre-order tree, -1 = absent child
 //   blk_meta   u32 [nblocks][4]           {tree_len, max_len, fmt, nsym}
+//   blk_keys   u32 [nblocks][256]         sorted merge keys, K2a -> K2b
+//   blk_nodes  u32 [nblocks][256][2]      merge nodes, K2b -> K2c
 #pragma once
 
 #include "common.cuh"
@@ -53,6 +55,8 @@ struct EncArgs {
     uint32_t *blk_table;
     int16_t *blk_tree;
     uint32_t *blk_meta;
+    uint32_t *blk_keys;   // [npass][256] sorted merge keys (enc_build.cuh)
+    uint32_t *blk_nodes;  // [npass][256][2] merge nodes: left | right << 16, leaves below
     uint32_t *status;  // [0] error code, [1] detail
 };
 

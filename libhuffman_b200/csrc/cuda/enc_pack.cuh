@@ -1,0 +1,194 @@
+// enc_pack.cuh — K3 fast lane: bit packing for blocks whose longest code word is <= 16 bits
+// (every block of ordinary data; deeper trees take k_pack_wide in enc_kernels.cuh).
+//
+// One warp per segment, 16 symbols per lane and iteration.  Code words are looked up as
+// {left-aligned code, length} pairs with one 8-byte shared-memory load, two neighbours are
+// concatenated in registers (<= 32 bits), the lane's bit offset comes from a warp scan of the
+// lengths, and finished 32-bit words are OR-ed into a zeroed staging window with shared-memory
+// atomics, so lanes that share a word need no hand-over protocol.  Whole words leave as
+// coalesced big-endian 32-bit stores; only the first and last bytes of a segment, which share a
+// word with a neighbouring segment, are written byte-wise.
+// Replaces __huf_encode_block + huf_bit_write (reference src/encoder.c:85-131,
+// src/bufio.c:18-32) and the header writes (src/encoder.c:325-342).
+#pragma once
+
+#include "enc_kernels.cuh"
+
+namespace hufb200 {
+
+constexpr uint32_t kPackFastMaxLen = 16;
+constexpr int kPackStageWords = 288;  // 16 symbols x 16 bits x 32 lanes = 256 words + carry, padded
+
+struct PackFastSmem {
+    uint2 table[kEncWarps][256];               // {code << (32 - len), len}
+    __align__(16) uint32_t stage[kEncWarps][kPackStageWords];
+};
+
+__device__ __forceinline__ void acc_put_or(BitAcc &s, uint32_t *stage, uint32_t t, uint32_t l)
+{
+    s.hi |= t >> s.nb;
+    s.lo |= __funnelshift_r(0u, t, s.nb);
+    s.nb += l;
+    if (s.nb >= 32) {
+        atomicOr(&stage[s.widx], s.hi);
+        s.hi = s.lo;
+        s.lo = 0;
+        s.nb -= 32;
+        s.widx++;
+    }
+}
+
+__global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
+{
+    __shared__ PackFastSmem sm;
+    const int lane = lane_id();
+    const int w = warp_in_cta();
+    const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
+    if (g >= a.npass * a.nspb) return;
+    if (a.status[0] != kOk) return;
+
+    const uint64_t bl = g / a.nspb;
+    const uint32_t *meta = a.blk_meta + bl * 4;
+    if (meta[1] > kPackFastMaxLen) return;  // k_pack_wide takes this block
+    const uint64_t b = a.blk0 + bl;
+    const uint32_t k = (uint32_t)(g % a.nspb);
+    const uint64_t blen = blk_len_of(a, b);
+    const uint64_t soff = (uint64_t)k * a.seg;
+    if (soff >= blen) return;
+    const uint32_t slen = (uint32_t)((blen - soff) < a.seg ? (blen - soff) : a.seg);
+    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
+    const uint8_t *blk_in = a.in + b * a.blocksize;
+    const uint8_t *p = blk_in + soff;
+
+    const uint32_t tree_len = meta[0];
+    const uint64_t boff = a.blk_off[b];
+    const uint64_t pay0 = boff + kHdrFixed + 2ull * tree_len;  // first payload byte
+    const uint64_t bits_total = a.blk_bits[bl];
+    const uint64_t o = a.seg_bitoff[g];
+    const bool last_seg = (k + 1 == nseg_b);
+    const uint64_t o_end = last_seg ? bits_total : a.seg_bitoff[g + 1];
+
+    // block header: written by the warp that owns segment 0
+    if (k == 0) {
+        const int16_t *tree = a.blk_tree + bl * kTreeStride;
+        const uint32_t hlen = kHdrFixed + 2 * tree_len;
+        uint8_t *dst = a.out + boff;
+        for (uint32_t i = lane; i < hlen; i += 32) {
+            uint32_t v;
+            if (i < 8) {
+                v = (uint32_t)(blen >> (8 * i));
+            } else if (i < 10) {
+                v = tree_len >> (8 * (i - 8));
+            } else {
+                v = (uint32_t)(uint16_t)tree[(i - 10) >> 1] >> (8 * (i & 1));
+            }
+            dst[i] = (uint8_t)v;
+        }
+    }
+
+    // per-warp copy of the code table, split into {code, length}
+    uint2 *tab = sm.table[w];
+    {
+        const uint32_t *src = a.blk_table + bl * 512;
+        for (int i = lane; i < 256; i += 32) {
+            const uint32_t e = src[i];
+            tab[i] = make_uint2(e & ~31u, e & 31u);
+        }
+    }
+    uint32_t *stage = sm.stage[w];
+    for (int i = lane; i < kPackStageWords / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+
+    OutRange r;
+    r.out = a.out;
+    r.b0 = pay0 + (o >> 3);
+    r.b1 = last_seg ? pay0 + ((bits_total + 7) >> 3) : pay0 + (o_end >> 3);
+    r.full_lo = (r.b0 + 3) >> 2;
+    r.full_hi = r.b1 >> 2;
+
+    // Global bit cursor.  The first byte of the segment may begin with the last bits of the
+    // previous segment's final code words: rebuild them so this warp owns the whole byte.
+    uint64_t gbit = (pay0 << 3) + o;
+    uint32_t q = (uint32_t)(gbit & 31);
+    uint64_t wbase = gbit >> 5;
+    {
+        const uint32_t rb = (uint32_t)(o & 7);
+        if (rb && lane == 0) {
+            uint32_t val = 0, got = 0;
+            uint64_t idx = soff;
+            while (got < rb) {
+                idx--;
+                const uint2 e = tab[blk_in[idx]];
+                val |= (e.x >> (32 - e.y)) << got;
+                got += e.y;
+            }
+            val &= (1u << rb) - 1u;
+            stage[0] = val << (32 - q);
+        }
+    }
+    __syncwarp();
+
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    for (uint32_t base = 0; base < slen; base += 512) {
+        // ---- this lane's 16 symbols
+        const uint32_t my0 = base + lane * 16;
+        uint32_t sym[4] = {0, 0, 0, 0};
+        uint32_t nvalid = 0;
+        if (my0 < slen) nvalid = min(16u, slen - my0);
+        if (aligned && nvalid == 16) {
+            const uint4 v = ld_stream_u4(p + my0);
+            sym[0] = v.x; sym[1] = v.y; sym[2] = v.z; sym[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((uint32_t)j < nvalid) sym[j >> 2] |= (uint32_t)p[my0 + j] << (8 * (j & 3));
+            }
+        }
+        // ---- look up, concatenate neighbours (<= 32 bits), sum the lengths
+        uint32_t t[8], lp[8], total_l = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t s0 = (sym[j >> 1] >> (16 * (j & 1))) & 0xffu;
+            const uint32_t s1 = (sym[j >> 1] >> (16 * (j & 1) + 8)) & 0xffu;
+            uint2 e0 = tab[s0], e1 = tab[s1];
+            if ((uint32_t)(2 * j) >= nvalid) e0 = make_uint2(0, 0);
+            if ((uint32_t)(2 * j + 1) >= nvalid) e1 = make_uint2(0, 0);
+            t[j] = e0.x | (e1.x >> e0.y);
+            lp[j] = e0.y + e1.y;
+            total_l += lp[j];
+        }
+        const uint32_t incl = warp_incl_scan(total_l);
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        const uint32_t start = q + incl - total_l;
+        BitAcc acc;
+        acc.hi = acc.lo = 0;
+        acc.nb = start & 31;
+        acc.widx = start >> 5;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc_put_or(acc, stage, t[j], lp[j]);
+        if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
+        __syncwarp();
+
+        // ---- copy finished words out, coalesced
+        const uint32_t nfull = (q + total) >> 5;
+        if (wbase >= r.full_lo && wbase + nfull <= r.full_hi) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(r.out) + wbase;
+            for (uint32_t i = lane; i < nfull; i += 32) dst[i] = bswap32(stage[i]);
+        } else {
+            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
+        }
+        const uint32_t carry = stage[nfull];  // unfinished word behind the full ones
+        q = (q + total) & 31;
+        wbase += nfull;
+        __syncwarp();
+        // ---- clear the window, keep the unfinished word in front
+        for (uint32_t i = lane; i <= (nfull >> 2); i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (lane == 0) stage[0] = carry;
+        __syncwarp();
+    }
+    // trailing partial word: only its owned bytes are written
+    if (q && lane == 0) store_word(r, wbase, stage[0]);
+}
+
+}  // namespace hufb200

@@ -11,6 +11,7 @@
 #include "dec_kernels.cuh"
 #include "dec_fast.cuh"
 #include "enc_kernels.cuh"
+#include "enc_build.cuh"
 
 using namespace hufb200;
 
@@ -33,6 +34,12 @@ using namespace hufb200;
         }                                                                          \
         HUF_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);                \
         if (t__) cudaEventRecord(t__->t1, (stream));                               \
+        if ((c)->debug) {                                                          \
+            cudaError_t le__ = cudaPeekAtLastError();                              \
+            if (le__ != cudaSuccess)                                               \
+                fprintf(stderr, "huf_b200: launch of %s failed: %s\n", #kernel,    \
+                        cudaGetErrorString(le__));                                 \
+        }                                                                          \
         (c)->launches++;                                                           \
     } while (0)
 
@@ -88,6 +95,7 @@ struct huf_b200_ctx {
     uint64_t *h_result = nullptr;   // pinned mirror, [32]
     uint64_t launches = 0;
     int accept_1025 = 0;
+    bool debug = false;             // HUF_B200_DEBUG: report failing launches on stderr
 
     // optional per-kernel timing (HUF_B200_OPT_KERNEL_TIMING): events around every launch
     bool timing = false;
@@ -109,6 +117,7 @@ struct huf_b200_ctx {
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
     uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode_slow
+    bool slow_ready = false;        // k_decode_slow attribute set
     bool fast_ready = false;        // k_decode attributes set
     int fast_per_sm = 1;
     uint64_t dec_stage_want = 80 * 1024;  // payload bytes of one block staged in shared memory
@@ -116,8 +125,10 @@ struct huf_b200_ctx {
 
 namespace {
 
-huf_error_t cuda_fail(cudaError_t e)
+huf_error_t cuda_fail(cudaError_t e, int line = 0)
 {
+    if (getenv("HUF_B200_DEBUG"))
+        fprintf(stderr, "huf_b200: CUDA error %d (%s) at huf_b200.cu:%d\n", (int)e, cudaGetErrorString(e), line);
     cudaGetLastError();
     return e == cudaErrorMemoryAllocation ? HUF_ERROR_MEMORY_ALLOCATION : HUF_ERROR_FATAL;
 }
@@ -125,7 +136,7 @@ huf_error_t cuda_fail(cudaError_t e)
 #define CU_TRY(expr)                                   \
     do {                                               \
         cudaError_t e__ = (expr);                      \
-        if (e__ != cudaSuccess) return cuda_fail(e__); \
+        if (e__ != cudaSuccess) return cuda_fail(e__, __LINE__); \
     } while (0)
 
 struct DeviceGuard {
@@ -188,6 +199,7 @@ huf_error_t huf_b200_ctx_create(huf_b200_ctx_t **out, int device)
     c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     const char *env = getenv("HUF_B200_ACCEPT_1025");
     c->accept_1025 = env && env[0] == '1';
+    c->debug = getenv("HUF_B200_DEBUG") != nullptr;
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_status, 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_result, 16 * sizeof(uint64_t));
@@ -324,6 +336,8 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     need += Arena::padded(per_pass * 512 * sizeof(uint32_t));    // blk_table
     need += Arena::padded(per_pass * kTreeStride * sizeof(int16_t));
     need += Arena::padded(per_pass * 4 * sizeof(uint32_t));
+    need += Arena::padded(per_pass * 256 * sizeof(uint32_t));
+    need += Arena::padded(per_pass * 512 * sizeof(uint32_t));
     if (!c->enc_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
     a.seg_hist = c->enc_ws.take<uint16_t>(nseg_pass * 256);
     a.seg_bitoff = c->enc_ws.take<uint64_t>(nseg_pass);
@@ -333,6 +347,8 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     a.blk_table = c->enc_ws.take<uint32_t>(per_pass * 512);
     a.blk_tree = c->enc_ws.take<int16_t>(per_pass * kTreeStride);
     a.blk_meta = c->enc_ws.take<uint32_t>(per_pass * 4);
+    a.blk_keys = c->enc_ws.take<uint32_t>(per_pass * 256);
+    a.blk_nodes = c->enc_ws.take<uint32_t>(per_pass * 512);
     a.status = c->d_status;
     c->d_blk_off = a.blk_off;
 
@@ -347,9 +363,12 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
         const unsigned bld_grid = (unsigned)((a.npass + kBuildWarps - 1) / kBuildWarps);
 
         CTX_LAUNCH(c, k_seg_hist, seg_grid, kEncWarps * 32, 0, st, a);
-        if (blocksize <= kW32MaxBlock)
-            CTX_LAUNCH(c, k_build<uint32_t>, bld_grid, kBuildWarps * 32, 0, st, a);
-        else
+        if (blocksize <= kW32MaxBlock) {
+            // sort (warp per block), exact merge (lane per block), codes + tree (warp per block)
+            CTX_LAUNCH(c, k_build_sort, bld_grid, kBuildWarps * 32, 0, st, a);
+            CTX_LAUNCH(c, k_build_merge, (unsigned)((a.npass + 31) / 32), 32, kMergeDyn, st, a);
+            CTX_LAUNCH(c, k_build_codes, bld_grid, kBuildWarps * 32, 0, st, a);
+        } else
             CTX_LAUNCH(c, k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, st, a);
         CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
                    a.npass, a.out_cap, a.status);
@@ -458,11 +477,14 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         if (want > max_dyn) want = max_dyn;
         if (want < 20480) want = 20480;  // the terminal list of the table build lives here
         want &= ~uint64_t(15);
-        if ((uint32_t)want != c->dec_stage) {
+        // the attribute belongs to the function, not to this context: always allow the maximum
+        // (other contexts in the process launch the same kernel with their own sizes)
+        if (!c->slow_ready) {
             CU_TRY(cudaFuncSetAttribute(k_decode_slow, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)want));
-            c->dec_stage = (uint32_t)want;
+                                        (int)(max_dyn & ~uint64_t(15))));
+            c->slow_ready = true;
         }
+        c->dec_stage = (uint32_t)want;
         a.stage_cap = c->dec_stage;
         int per_sm = 1;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_slow, kDecThreads,
