@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build(EncArgs a)
         atomicMax(&a.status[0], (uint32_t)kErrFatal);
         a.status[1] = max_len;
     }
+    if (max_len > 16 && lane == 0) atomicAdd(&a.status[2], 1u);  // k_pack_wide has work
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t s = lane + 32 * i;
@@ -539,7 +540,11 @@ __device__ __forceinline__ uint32_t pack_flush_carry(const BitAcc &acc, uint32_t
     return out;
 }
 
-__global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
+// General lane of K3: blocks whose longest code word exceeds kPackWideMinLen - 1 bits (the
+// fast lane in enc_pack.cuh takes all others); status[2] counts such blocks.
+constexpr uint32_t kPackWideMinLen = 17;
+
+__global__ void __launch_bounds__(kEncWarps * 32) k_pack_wide(EncArgs a)
 {
     __shared__ PackSmem sm;
     const int lane = lane_id();
@@ -547,8 +552,10 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
     if (g >= a.npass * a.nspb) return;
     if (a.status[0] != kOk) return;
+    if (a.status[2] == 0) return;  // no deep block in this call
 
     const uint64_t bl = g / a.nspb;
+    if (a.blk_meta[bl * 4 + 1] < kPackWideMinLen) return;
     const uint64_t b = a.blk0 + bl;
     const uint32_t k = (uint32_t)(g % a.nspb);
     const uint64_t blen = blk_len_of(a, b);

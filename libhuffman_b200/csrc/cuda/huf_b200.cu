@@ -12,6 +12,7 @@
 #include "dec_fast.cuh"
 #include "enc_kernels.cuh"
 #include "enc_build.cuh"
+#include "enc_pack.cuh"
 
 using namespace hufb200;
 
@@ -373,6 +374,7 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
         CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
                    a.npass, a.out_cap, a.status);
         CTX_LAUNCH(c, k_pack, seg_grid, kEncWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_pack_wide, seg_grid, kEncWarps * 32, 0, st, a);
     }
     CU_TRY(cudaGetLastError());
     // result: total size + status, copied to the pinned mirror on the same stream
