@@ -4,7 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include <huffman/b200.h>
 
@@ -164,6 +167,68 @@ uint32_t pick_seg(uint64_t blocksize)
     uint64_t s = blocksize < kSegMax ? blocksize : kSegMax;
     s = (s + 15) & ~uint64_t(15);
     return (uint32_t)(s ? s : 16);
+}
+
+// ---- staged host <-> device copies ---------------------------------------------------------
+
+constexpr uint64_t kStageChunk = 32ull << 20;  // bytes per pinned bounce buffer
+constexpr uint64_t kStageMin = 8ull << 20;     // smaller copies go straight through cudaMemcpy
+
+struct StagePool {
+    std::mutex mu;
+    bool tried = false, ok = false;
+    uint8_t *pin[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    cudaStream_t stream = nullptr;
+    unsigned threads = 1;
+};
+StagePool g_stage;
+
+bool stage_ready()
+{
+#ifdef HUF_EMU
+    return false;  // kernel-logic emulation: plain copies
+#else
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    if (g_stage.tried) return g_stage.ok;
+    g_stage.tried = true;
+    cudaError_t e = cudaStreamCreateWithFlags(&g_stage.stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaHostAlloc(reinterpret_cast<void **>(&g_stage.pin[i]), kStageChunk, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_stage.done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(g_stage.done[i], g_stage.stream);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    const char *env = getenv("HUF_B200_COPY_THREADS");
+    unsigned want = env ? (unsigned)atoi(env) : 8u;
+    if (hc && want > hc) want = hc;
+    g_stage.threads = want ? want : 1;
+    g_stage.ok = true;
+    return true;
+#endif
+}
+
+void parallel_memcpy(void *dst, const void *src, uint64_t bytes)
+{
+    const unsigned nt = g_stage.threads;
+    if (nt <= 1 || bytes < (4ull << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const uint64_t slice = ((bytes + nt - 1) / nt + 4095) & ~uint64_t(4095);
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nt; t++) {
+        const uint64_t at = (uint64_t)t * slice;
+        if (at >= bytes) break;
+        const uint64_t len = bytes - at < slice ? bytes - at : slice;
+        pool.emplace_back([=] { memcpy(static_cast<uint8_t *>(dst) + at, static_cast<const uint8_t *>(src) + at, len); });
+    }
+    memcpy(dst, src, bytes < slice ? bytes : slice);
+    for (auto &th : pool) th.join();
 }
 
 }  // namespace
@@ -641,15 +706,58 @@ huf_error_t huf_b200_dev_free(void *d_ptr)
     return HUF_ERROR_SUCCESS;
 }
 
+// Host <-> device copies of caller-owned (pageable) memory.  Large copies run as a two-deep
+// pipeline over pinned bounce buffers: the DMA of one chunk overlaps the host-side memcpy of
+// the next, and that memcpy is split over a few threads (a freshly allocated destination is
+// first-touched by all of them instead of page-faulting on one core).
 huf_error_t huf_b200_copy_h2d(void *d_dst, const void *h_src, uint64_t bytes)
 {
-    if (bytes) CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    if (!bytes) return HUF_ERROR_SUCCESS;
+    if (bytes < kStageMin || !stage_ready()) {
+        CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+        return HUF_ERROR_SUCCESS;
+    }
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    const uint8_t *src = static_cast<const uint8_t *>(h_src);
+    uint8_t *dst = static_cast<uint8_t *>(d_dst);
+    int k = 0;
+    for (uint64_t at = 0; at < bytes; at += kStageChunk, k ^= 1) {
+        const uint64_t len = bytes - at < kStageChunk ? bytes - at : kStageChunk;
+        CU_TRY(cudaEventSynchronize(g_stage.done[k]));  // the DMA that last used this buffer
+        parallel_memcpy(g_stage.pin[k], src + at, len);
+        CU_TRY(cudaMemcpyAsync(dst + at, g_stage.pin[k], len, cudaMemcpyHostToDevice, g_stage.stream));
+        CU_TRY(cudaEventRecord(g_stage.done[k], g_stage.stream));
+    }
+    CU_TRY(cudaStreamSynchronize(g_stage.stream));
     return HUF_ERROR_SUCCESS;
 }
 
 huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
 {
-    if (bytes) CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    if (!bytes) return HUF_ERROR_SUCCESS;
+    if (bytes < kStageMin || !stage_ready()) {
+        CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+        return HUF_ERROR_SUCCESS;
+    }
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    uint8_t *dst = static_cast<uint8_t *>(h_dst);
+    const uint8_t *src = static_cast<const uint8_t *>(d_src);
+    const uint64_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
+    auto issue = [&](uint64_t c) -> cudaError_t {
+        const uint64_t at = c * kStageChunk;
+        const uint64_t len = bytes - at < kStageChunk ? bytes - at : kStageChunk;
+        cudaError_t e = cudaMemcpyAsync(g_stage.pin[c & 1], src + at, len, cudaMemcpyDeviceToHost, g_stage.stream);
+        if (e == cudaSuccess) e = cudaEventRecord(g_stage.done[c & 1], g_stage.stream);
+        return e;
+    };
+    CU_TRY(issue(0));
+    for (uint64_t c = 0; c < nchunk; c++) {
+        const uint64_t at = c * kStageChunk;
+        const uint64_t len = bytes - at < kStageChunk ? bytes - at : kStageChunk;
+        CU_TRY(cudaEventSynchronize(g_stage.done[c & 1]));
+        if (c + 1 < nchunk) CU_TRY(issue(c + 1));  // next DMA overlaps this memcpy
+        parallel_memcpy(dst + at, g_stage.pin[c & 1], len);
+    }
     return HUF_ERROR_SUCCESS;
 }
 
