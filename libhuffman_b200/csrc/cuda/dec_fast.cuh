@@ -55,11 +55,11 @@ constexpr uint32_t kFastFlags = 0xc0u;
 // length, [31:16] number of terminals; [1] number of long-code records
 constexpr uint32_t kMetaFast = 1u;
 
-constexpr int kFT = 512;                  // threads per CTA
-constexpr int kRegStride = 124;           // bytes per thread region (31 words: conflict-free)
+constexpr int kFT = 256;                  // threads per CTA
+constexpr int kRegStride = 252;           // bytes per thread region (63 words: conflict-free)
 constexpr int kRegPad = 12;               // room in front of the speculative symbols
-constexpr int kRegCap = 112;              // symbols a region can hold behind the pad
-constexpr int kMaxSubWords = 15;          // payload words per thread per chunk (odd)
+constexpr int kRegCap = 240;              // symbols a region can hold behind the pad
+constexpr int kMaxSubWords = 29;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
         const uint64_t out0 = a.out_off[j];
         const bool can_write = !a.count_only && out0 + orig_len <= a.out_cap;
         uint32_t sub_cap_w = min((uint32_t)kMaxSubWords, (kRegCap * min_len) / 32u);
-        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 3, so never below 3
+        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 7, so never below 7
         // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
         uint32_t warm = 160;
         if (use_guess) {
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             const uint32_t per_word = nch * (uint32_t)kFT * 32u;
             uint32_t subw = (span + per_word - 1) / per_word;
             subw |= 1u;
-            if (subw < 3) subw = 3;
+            if (subw < 7) subw = 7;
             if (subw > sub_cap_w) subw = sub_cap_w;
             const uint32_t sub = subw * 32u;
             const uint64_t lim_rel = limit - 8ull * base16;
