@@ -55,11 +55,11 @@ constexpr uint32_t kFastFlags = 0xc0u;
 // length, [31:16] number of terminals; [1] number of long-code records
 constexpr uint32_t kMetaFast = 1u;
 
-constexpr int kFT = 256;                  // threads per CTA
-constexpr int kRegStride = 252;           // bytes per thread region (63 words: conflict-free)
+constexpr int kFT = 128;                  // threads per CTA
+constexpr int kRegStride = 236;           // bytes per thread region (59 words: conflict-free)
 constexpr int kRegPad = 12;               // room in front of the speculative symbols
-constexpr int kRegCap = 240;              // symbols a region can hold behind the pad
-constexpr int kMaxSubWords = 29;          // payload words per thread per chunk (odd)
+constexpr int kRegCap = 224;              // symbols a region can hold behind the pad
+constexpr int kMaxSubWords = 27;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
