@@ -64,6 +64,16 @@ __device__ __forceinline__ void cp_async_wait_all()
 #endif
 }
 
+// Hint: bring the 128-byte line at p into L2 (no register, no stall).
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+#ifndef HUF_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
 template <typename T>

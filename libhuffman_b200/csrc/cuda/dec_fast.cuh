@@ -64,7 +64,8 @@ constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
 
-constexpr int kTreeHdrStride = 2068;      // staged header bytes per candidate (517 words, odd)
+constexpr int kTreeWin = 520;             // serialised tree elements staged per lane at a time
+constexpr int kTreeHdrStride = 1052;      // staged bytes per candidate (263 words, odd)
 constexpr int kTreeDyn = 32 * kTreeHdrStride;
 
 // ------------------------------------------------------------------------------------------
@@ -103,118 +104,138 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
             }
             my_ok = ok;
         }
-        // ... then the warp stages the 32 serialised trees: whole aligned words copied verbatim,
-        // asynchronously, all in flight together
-        for (int c = 0; c < 32; c++) {
-            if (!__shfl_sync(kFull, (int)my_ok, c)) continue;
-            const uint64_t b0 = __shfl_sync(kFull, my_off, c) + kHdrFixed;
-            const uint32_t tl = __shfl_sync(kFull, my_tl, c);
-            const uint64_t w0 = b0 >> 2, w1 = (b0 + 2ull * tl + 3) >> 2;  // word range
-            uint32_t *dst = reinterpret_cast<uint32_t *>(hdr + c * kTreeHdrStride);
-            for (uint64_t k = w0 + lane; k < w1; k += 32) {
-                if (4 * k + 4 <= a.avail) {
-                    cp_async4(dst + (k - w0), reinterpret_cast<const uint32_t *>(a.in) + k);
-                } else {
-                    uint32_t v = 0;
-                    for (int q = 0; q < 4; q++) {
-                        if (4 * k + q < a.avail) v |= (uint32_t)a.in[4 * k + q] << (8 * q);
-                    }
-                    dst[k - w0] = v;
-                }
-            }
-        }
-        cp_async_wait_all();
-        __syncwarp();
-        const uint32_t my_skew = (uint32_t)((my_off + kHdrFixed) & 3);
-
-        // ---- every lane walks its own tree
+        // ---- walk state of my tree (kept across window reloads)
         const uint64_t j = g0 + lane;
         uint32_t meta = 0, nlong = 0;
-        if (j < ncand && my_ok && my_ol) {
-            const uint32_t *hw = reinterpret_cast<const uint32_t *>(hdr + lane * kTreeHdrStride);
-            const uint32_t tl = my_tl;
-            // Elements i, i+1, i+2 (sign-extended; past tree_len they read as absent children,
-            // src/tree.c:154-160).  The staged words keep the stream's byte skew: three words
-            // and two funnel shifts deliver four consecutive elements.
-            auto elems3 = [&](uint32_t i, int &x0, int &x1, int &x2) {
-                const uint32_t byte = my_skew + 2 * i;
-                const uint32_t w = byte >> 2, sh = (byte & 3) * 8;
-                const uint32_t a0 = hw[w], a1 = hw[w + 1], a2 = hw[w + 2];
-                const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                x0 = i < tl ? (int)(int16_t)(lo & 0xffffu) : -1;
-                x1 = i + 1 < tl ? (int)(int16_t)(lo >> 16) : -1;
-                x2 = i + 2 < tl ? (int)(int16_t)(hi & 0xffffu) : -1;
-            };
-            uint32_t *slot = a.terms + j * kTermStride;
-            // Ancestors whose right slot is still open, one bit per depth: every node opens its
-            // right slot exactly once, so the pending stack is a bit mask and a pop is a clz.
-            uint64_t pend = 1;            // the root, depth 0
-            uint32_t i = 1, D = 1;        // slot being filled: depth D ...
-            uint64_t C = 0;               // ... reached by the path bits C
-            uint32_t nterm = 0, min_len = kTreeReach + 1;
-            int e, e1, e2;
-            elems3(0, e, e1, e2);
-            bool ok = e != -1 && e1 != -1;  // a root with something below its left edge
-            while (ok) {
-                elems3(i, e, e1, e2);
-                bool pop;
-                if (e != -1) {
-                    if (e1 == -1 && e2 == -1) {  // leaf: v, absent, absent
-                        if (D <= (uint32_t)kTreeReach) {
-                            if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                            slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) |
-                                            ((uint32_t)(e & 0xff) << 8) | D;
-                            min_len = min(min_len, D);
+        bool active = j < ncand && my_ok && my_ol;  // still walking
+        bool ok = active;
+        const uint32_t tl = my_tl;
+        uint32_t *slot = a.terms + j * kTermStride;
+        // Ancestors whose right slot is still open, one bit per depth: every node opens its
+        // right slot exactly once, so the pending stack is a bit mask and a pop is a clz.
+        uint64_t pend = 1;            // the root, depth 0
+        uint32_t i = 1, D = 1;        // slot being filled: depth D ...
+        uint64_t C = 0;               // ... reached by the path bits C
+        uint32_t nterm = 0, min_len = kTreeReach + 1;
+        uint32_t wb = 0;              // first element of my staged window
+        bool first = true;
+
+        while (__any_sync(kFull, active)) {
+            // ---- the warp stages a window of kTreeWin elements for every walking lane: whole
+            // aligned words copied verbatim, asynchronously, all in flight together
+            for (int c = 0; c < 32; c++) {
+                if (!__shfl_sync(kFull, (int)active, c)) continue;
+                const uint64_t b0 = __shfl_sync(kFull, my_off, c) + kHdrFixed + 2ull * __shfl_sync(kFull, wb, c);
+                const uint32_t left = __shfl_sync(kFull, tl, c) - __shfl_sync(kFull, wb, c);
+                const uint32_t cnt = left < (uint32_t)kTreeWin ? left : (uint32_t)kTreeWin;
+                const uint64_t w0 = b0 >> 2, w1 = (b0 + 2ull * cnt + 3) >> 2;  // word range
+                uint32_t *dst = reinterpret_cast<uint32_t *>(hdr + c * kTreeHdrStride);
+                for (uint64_t k = w0 + lane; k < w1; k += 32) {
+                    if (4 * k + 4 <= a.avail) {
+                        cp_async4(dst + (k - w0), reinterpret_cast<const uint32_t *>(a.in) + k);
+                    } else {
+                        uint32_t v = 0;
+                        for (int q = 0; q < 4; q++) {
+                            if (4 * k + q < a.avail) v |= (uint32_t)a.in[4 * k + q] << (8 * q);
+                        }
+                        dst[k - w0] = v;
+                    }
+                }
+            }
+            cp_async_wait_all();
+            __syncwarp();
+
+            if (active) {
+                const uint32_t *hw = reinterpret_cast<const uint32_t *>(hdr + lane * kTreeHdrStride);
+                const uint32_t skew = (uint32_t)((my_off + kHdrFixed + 2ull * wb) & 3);
+                // Elements i, i+1, i+2 (sign-extended; past tree_len they read as absent
+                // children, src/tree.c:154-160).  The staged words keep the stream's byte skew:
+                // three words and two funnel shifts deliver four consecutive elements.
+                auto elems3 = [&](uint32_t at, int &x0, int &x1, int &x2) {
+                    const uint32_t byte = skew + 2 * (at - wb);
+                    const uint32_t w = byte >> 2, sh = (byte & 3) * 8;
+                    const uint32_t a0 = hw[w], a1 = hw[w + 1], a2 = hw[w + 2];
+                    const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                    x0 = at < tl ? (int)(int16_t)(lo & 0xffffu) : -1;
+                    x1 = at + 1 < tl ? (int)(int16_t)(lo >> 16) : -1;
+                    x2 = at + 2 < tl ? (int)(int16_t)(hi & 0xffffu) : -1;
+                };
+                int e, e1, e2;
+                if (first) {
+                    elems3(0, e, e1, e2);
+                    ok = e != -1 && e1 != -1;  // a root with something below its left edge
+                    first = false;
+                }
+                while (ok) {
+                    // elements i .. i+2 must lie in the window (or past the end of the tree)
+                    if (i + 3 > wb + (uint32_t)kTreeWin && wb + (uint32_t)kTreeWin < tl) {
+                        wb = i;  // slide the window; the warp reloads it
+                        break;
+                    }
+                    elems3(i, e, e1, e2);
+                    // the right slot of the root must stay empty (table sits behind the root bit)
+                    if (D == 1 && C == 1 && e != -1) {
+                        ok = false;
+                        break;
+                    }
+                    bool pop;
+                    if (e != -1) {
+                        if (e1 == -1 && e2 == -1) {  // leaf: v, absent, absent
+                            if (D <= (uint32_t)kTreeReach) {
+                                if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
+                                slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) |
+                                                ((uint32_t)(e & 0xff) << 8) | D;
+                                min_len = min(min_len, D);
+                            } else {
+                                if (nlong >= (uint32_t)kLongMax || nterm + 2 * nlong + 3 > (uint32_t)kTermStride) {
+                                    ok = false;
+                                    break;
+                                }
+                                slot[kTermStride - 2 * (nlong + 1)] = (uint32_t)(C << (kLongBits - D));
+                                slot[kTermStride - 2 * (nlong + 1) + 1] = (D << 8) | (uint32_t)(e & 0xff);
+                                nlong++;
+                            }
+                            i += 3;
+                            pop = true;
                         } else {
-                            if (nlong >= (uint32_t)kLongMax || nterm + 2 * nlong + 3 > (uint32_t)kTermStride) {
+                            if (D >= (uint32_t)kLongBits) {  // leaves below would need more than 32 bits
                                 ok = false;
                                 break;
                             }
-                            slot[kTermStride - 2 * (nlong + 1)] = (uint32_t)(C << (kLongBits - D));
-                            slot[kTermStride - 2 * (nlong + 1) + 1] = (D << 8) | (uint32_t)(e & 0xff);
-                            nlong++;
+                            if (D == (uint32_t)kTreeReach) {  // inner node at the table depth: long codes
+                                if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
+                                slot[nterm++] = ((uint32_t)C << 16) | kFastLong;
+                            }
+                            pend |= 1ull << D;
+                            i++;
+                            D++;
+                            C <<= 1;
+                            pop = false;
                         }
-                        i += 3;
-                        pop = true;
                     } else {
-                        if (D >= (uint32_t)kLongBits) {  // leaves below would need more than 32 bits
+                        // consuming bit D walks into an absent child; below the table such a walk
+                        // simply matches no long-code record
+                        if (D <= (uint32_t)kTreeReach) {
+                            if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
+                            slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) | kFastDead;
+                        }
+                        i++;
+                        pop = true;
+                    }
+                    if (pop) {
+                        if (pend == 0) {  // every slot filled: the tree is complete
+                            meta = kMetaFast | (min_len << 8) | (nterm << 16);
                             ok = false;
                             break;
                         }
-                        if (D == (uint32_t)kTreeReach) {  // inner node at the table depth: long codes
-                            if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                            slot[nterm++] = ((uint32_t)C << 16) | kFastLong;
-                        }
-                        pend |= 1ull << D;
-                        i++;
-                        D++;
-                        C <<= 1;
-                        pop = false;
-                    }
-                } else {
-                    // consuming bit D walks into an absent child; below the table such a walk
-                    // simply matches no long-code record
-                    if (D <= (uint32_t)kTreeReach) {
-                        if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                        slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) | kFastDead;
-                    }
-                    i++;
-                    pop = true;
-                }
-                if (pop) {
-                    if (pend == 0) break;  // every slot filled: the tree is complete
-                    const uint32_t d = 63u - (uint32_t)__clzll((long long)pend);  // deepest open right slot
-                    pend &= ~(1ull << d);
-                    C = ((C >> (D - d)) << 1) | 1u;
-                    D = d + 1;
-                    // the right slot of the root must stay empty (table sits behind the root bit)
-                    if (d == 0) {
-                        elems3(i, e, e1, e2);
-                        if (e != -1) ok = false;
+                        const uint32_t d = 63u - (uint32_t)__clzll((long long)pend);  // deepest open right slot
+                        pend &= ~(1ull << d);
+                        C = ((C >> (D - d)) << 1) | 1u;
+                        D = d + 1;
                     }
                 }
+                if (!ok) active = false;
             }
-            if (ok) meta = kMetaFast | (min_len << 8) | (nterm << 16);
         }
         if (j < ncand) {
             a.meta[2 * j] = meta;
@@ -389,6 +410,12 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
         }
         const uint32_t min_len = (meta >> 8) & 0xffu;
         const uint32_t nterm = meta >> 16;
+        // the block this CTA decodes next: request its header, terminals and first chunk into L2
+        if (j + gridDim.x < ncand) {
+            const uint64_t noff = a.cand[j + gridDim.x] + 128ull * (uint32_t)tid;
+            if (noff < a.avail) prefetch_l2(a.in + noff);
+            if (tid < 26) prefetch_l2(a.terms + (j + gridDim.x) * kTermStride + 32 * tid);
+        }
 
         // ---- lookup table from the ordered terminal list: every thread fills 16 entries
         {
@@ -484,8 +511,11 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             // threads whose sub-block starts inside the covered bits take part in this chunk
             const uint32_t nact = (cover - A + sub - 1) / sub;
 
-            // (0) stage the chunk: 16-byte loads, bytes past `avail` read as zero
+            // (0) stage the chunk: 16-byte loads, bytes past `avail` read as zero; the lines of
+            // the chunk behind it are requested into L2 meanwhile
             {
+                const uint64_t nxt = base16 + ((cover + 7) >> 3) + 128ull * (uint32_t)tid;
+                if (nxt < a.avail && 128u * (uint32_t)tid < (kFT * sub >> 3) + 256u) prefetch_l2(a.in + nxt);
                 const uint32_t n16 = ((cover + 7) >> 3) / 16 + 2;
                 for (uint32_t c = tid; c < n16; c += kFT) {
                     const uint64_t byte = base16 + 16ull * c;

@@ -568,7 +568,7 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         }
         // fast lane: tree walk (one lane per candidate), chunked region decode; whatever it
         // declines goes through the general lane
-        CTX_LAUNCH(c, k_tree, c->sm_count * 3, 32, kTreeDyn, st, a);
+        CTX_LAUNCH(c, k_tree, c->sm_count * 6, 32, kTreeDyn, st, a);
         CTX_LAUNCH(c, k_decode, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
         CTX_LAUNCH(c, k_decode_slow, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
         CTX_LAUNCH(c, k_verify, 1, kScanThreads, 0, st, a);
