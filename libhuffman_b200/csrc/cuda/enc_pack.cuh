@@ -12,12 +12,14 @@
 // src/bufio.c:18-32) and the header writes (src/encoder.c:325-342).
 #pragma once
 
+#include <type_traits>
+
 #include "enc_kernels.cuh"
 
 namespace hufb200 {
 
 constexpr uint32_t kPackFastMaxLen = 16;
-constexpr int kPackStageWords = 288;  // 16 symbols x 16 bits x 32 lanes = 256 words + carry, padded
+constexpr int kPackStageWords = 288;  // 16 symbols x 16 bits x 32 lanes = 256 words + kept line, padded
 
 struct PackFastSmem {
     uint2 table[kEncWarps][256];               // {code << (32 - len), len}
@@ -106,11 +108,12 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     r.full_lo = (r.b0 + 3) >> 2;
     r.full_hi = r.b1 >> 2;
 
-    // Global bit cursor.  The first byte of the segment may begin with the last bits of the
-    // previous segment's final code words: rebuild them so this warp owns the whole byte.
-    uint64_t gbit = (pay0 << 3) + o;
-    uint32_t q = (uint32_t)(gbit & 31);
-    uint64_t wbase = gbit >> 5;
+    // Global bit cursor, kept relative to a 16-byte line of the output so that finished lines
+    // leave as 128-bit stores.  The first byte of the segment may begin with the last bits of
+    // the previous segment's final code words: rebuild them so this warp owns the whole byte.
+    const uint64_t gbit = (pay0 << 3) + o;
+    uint32_t q = (uint32_t)(gbit & 127);    // bits in front of the cursor inside its line
+    uint64_t wbase = (gbit >> 7) << 2;      // output word index of stage[0] (multiple of 4)
     {
         const uint32_t rb = (uint32_t)(o & 7);
         if (rb && lane == 0) {
@@ -123,22 +126,24 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
                 got += e.y;
             }
             val &= (1u << rb) - 1u;
-            stage[0] = val << (32 - q);
+            stage[q >> 5] = val << (32 - (q & 31));  // rb != 0 implies q & 31 != 0
         }
     }
     __syncwarp();
 
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    for (uint32_t base = 0; base < slen; base += 512) {
-        // ---- this lane's 16 symbols
+    // One iteration = 16 symbols per lane.  FULL: every lane has 16 symbols and the input is
+    // 16-byte aligned (all iterations but the last of a segment).
+    auto iteration = [&](auto full_tag, uint32_t base) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const uint32_t my0 = base + lane * 16;
         uint32_t sym[4] = {0, 0, 0, 0};
-        uint32_t nvalid = 0;
-        if (my0 < slen) nvalid = min(16u, slen - my0);
-        if (aligned && nvalid == 16) {
+        uint32_t nvalid = 16;
+        if (FULL) {
             const uint4 v = ld_stream_u4(p + my0);
             sym[0] = v.x; sym[1] = v.y; sym[2] = v.z; sym[3] = v.w;
         } else {
+            nvalid = my0 < slen ? min(16u, slen - my0) : 0u;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 if ((uint32_t)j < nvalid) sym[j >> 2] |= (uint32_t)p[my0 + j] << (8 * (j & 3));
@@ -148,11 +153,13 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         uint32_t t[8], lp[8], total_l = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const uint32_t s0 = (sym[j >> 1] >> (16 * (j & 1))) & 0xffu;
-            const uint32_t s1 = (sym[j >> 1] >> (16 * (j & 1) + 8)) & 0xffu;
+            const uint32_t s0 = __byte_perm(sym[j >> 1], 0, 0x4440 + 2 * (j & 1));
+            const uint32_t s1 = __byte_perm(sym[j >> 1], 0, 0x4441 + 2 * (j & 1));
             uint2 e0 = tab[s0], e1 = tab[s1];
-            if ((uint32_t)(2 * j) >= nvalid) e0 = make_uint2(0, 0);
-            if ((uint32_t)(2 * j + 1) >= nvalid) e1 = make_uint2(0, 0);
+            if (!FULL) {
+                if ((uint32_t)(2 * j) >= nvalid) e0 = make_uint2(0, 0);
+                if ((uint32_t)(2 * j + 1) >= nvalid) e1 = make_uint2(0, 0);
+            }
             t[j] = e0.x | (e1.x >> e0.y);
             lp[j] = e0.y + e1.y;
             total_l += lp[j];
@@ -169,26 +176,40 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
         __syncwarp();
 
-        // ---- copy finished words out, coalesced
-        const uint32_t nfull = (q + total) >> 5;
-        if (wbase >= r.full_lo && wbase + nfull <= r.full_hi) {
-            uint32_t *dst = reinterpret_cast<uint32_t *>(r.out) + wbase;
-            for (uint32_t i = lane; i < nfull; i += 32) dst[i] = bswap32(stage[i]);
-        } else {
-            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
+        // ---- finished 16-byte lines leave coalesced; the unfinished line stays in front
+        const uint32_t nlines = (q + total) >> 7;
+        for (uint32_t L = lane; L < nlines; L += 32) {
+            const uint64_t w0 = wbase + 4 * L;
+            const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
+            if (w0 >= r.full_lo && w0 + 4 <= r.full_hi) {
+                reinterpret_cast<uint4 *>(r.out)[w0 >> 2] =
+                    make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+            } else {
+                store_word(r, w0, v.x);
+                store_word(r, w0 + 1, v.y);
+                store_word(r, w0 + 2, v.z);
+                store_word(r, w0 + 3, v.w);
+            }
         }
-        const uint32_t carry = stage[nfull];  // unfinished word behind the full ones
-        q = (q + total) & 31;
-        wbase += nfull;
+        const uint32_t keep = lane < 4 ? stage[4 * nlines + lane] : 0u;
+        q = (q + total) & 127;
+        wbase += 4 * nlines;
         __syncwarp();
-        // ---- clear the window, keep the unfinished word in front
-        for (uint32_t i = lane; i <= (nfull >> 2); i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = lane; i <= nlines; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        if (lane == 0) stage[0] = carry;
+        if (lane < 4) stage[lane] = keep;
         __syncwarp();
+    };
+    const bool out_ok = (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    uint32_t base = 0;
+    if (aligned && out_ok) {
+        for (; base + 512 <= slen; base += 512) iteration(std::true_type{}, base);
     }
-    // trailing partial word: only its owned bytes are written
-    if (q && lane == 0) store_word(r, wbase, stage[0]);
+    for (; base < slen; base += 512) iteration(std::false_type{}, base);
+
+    // what is left of the last line: finished words and the trailing partial word, of which
+    // only the owned bytes are written
+    if (lane < 4 && 32 * (uint32_t)lane < q) store_word(r, wbase + lane, stage[lane]);
 }
 
 }  // namespace hufb200
