@@ -158,6 +158,24 @@ def cpu_reference_run(procs: int, mib_per_proc: int, nsym: int, blocksize: int, 
     return kind, nbytes * procs, per_round
 
 
+def workload_name(args) -> str:
+    """BASELINE.json configs[1]; both arms report the same string."""
+    return (f"{args.mib} MiB Zipf(1.1) over {args.nsym} symbols per GPU, {args.blocksize} B blocks, "
+            "huf_encode then huf_decode")
+
+
+def measured_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    ncu --set full capture (profiles/traffic.json), or None."""
+    f = ROOT / "profiles" / "traffic.json"
+    if not f.exists():
+        return None
+    try:
+        return json.loads(f.read_text()).get(kernel)
+    except (ValueError, OSError):
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -178,9 +196,10 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t / len(timed), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": f"Zipf(1.1) over {args.nsym} symbols, {args.blocksize} B blocks, encode+decode, "
-                               f"bounded sample of {mib} MiB per core per step",
-                   "blocksize": args.blocksize, "parallelism": f"{cores} processes over block ranges"},
+        "config": {"workload": workload_name(args), "blocksize": args.blocksize,
+                   "blocks_per_gpu": (args.mib << 20) // args.blocksize,
+                   "parallelism": f"{cores} host processes over block ranges (reference CPU path)",
+                   "sample": f"each step codes a bounded sample of the workload: {mib} MiB per process"},
         "encode_gbs": total * len(timed) / sum(e for e, _ in timed) / GB,
         "decode_gbs": total * len(timed) / sum(d for _, d in timed) / GB,
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
@@ -350,7 +369,7 @@ def run_b200_arm(args):
         if dom:
             achieved = algo / (kavg[dom] / 1e3) / GB
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": measured_traffic(dom), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo,
                     "kernel_ms": {k: round(v, 4) for k, v in sorted(kavg.items())},
                     "encode_path_frac": (n + csize) * args.steps / t_enc / GB / peak,
@@ -368,10 +387,9 @@ def run_b200_arm(args):
             "vs_baseline": None,
             "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{args.mib} MiB Zipf(1.1) over {args.nsym} symbols per GPU, "
-                                   f"{bs} B blocks, huf_encode then huf_decode, device resident",
-                       "blocksize": bs, "blocks_per_gpu": n // bs, "compressed_bytes_per_gpu": csize,
+            "config": {"workload": workload_name(args), "blocksize": bs, "blocks_per_gpu": n // bs, "compressed_bytes_per_gpu": csize,
                        "ratio": csize / n, "parallelism": f"block ranges x{world}, no collective",
+                       "residency": "device resident (inputs in HBM before the timed region)",
                        "l2": "inputs larger than L2 (1 GiB in, ~0.9 GiB stream)",
                        "decoder_mode": "strict (reference parity)" if args.nsym <= 255 else "accept_1025 opt-in"},
             "encode_gbs": n * world * args.steps / t_enc / GB,
