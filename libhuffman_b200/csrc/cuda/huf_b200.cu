@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -710,8 +711,35 @@ huf_error_t huf_b200_dev_free(void *d_ptr)
 // pipeline over pinned bounce buffers: the DMA of one chunk overlaps the host-side memcpy of
 // the next, and that memcpy is split over a few threads (a freshly allocated destination is
 // first-touched by all of them instead of page-faulting on one core).
+static double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+struct CopyTimer {
+    const char *what;
+    uint64_t bytes;
+    double t0;
+    bool on;
+    CopyTimer(const char *w, uint64_t b) : what(w), bytes(b), t0(0), on(getenv("HUF_B200_DEBUG") != nullptr)
+    {
+        if (on) t0 = now_s();
+    }
+    ~CopyTimer()
+    {
+        if (on && bytes >= (1u << 20)) {
+            const double dt = now_s() - t0;
+            fprintf(stderr, "huf_b200: %s %.1f MiB in %.1f ms (%.2f GB/s)\n", what, bytes / 1048576.0, dt * 1e3,
+                    bytes / dt / 1e9);
+        }
+    }
+};
+
 huf_error_t huf_b200_copy_h2d(void *d_dst, const void *h_src, uint64_t bytes)
 {
+    CopyTimer timer("copy_h2d", bytes);
     if (!bytes) return HUF_ERROR_SUCCESS;
     if (bytes < kStageMin || !stage_ready()) {
         CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
@@ -734,6 +762,7 @@ huf_error_t huf_b200_copy_h2d(void *d_dst, const void *h_src, uint64_t bytes)
 
 huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
 {
+    CopyTimer timer("copy_d2h", bytes);
     if (!bytes) return HUF_ERROR_SUCCESS;
     if (bytes < kStageMin || !stage_ready()) {
         CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
