@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             // (1) warm-up in front of my sub-block, then decode it into my region
             const uint32_t my_lo = tid == 0 ? rel_start : min(A + (uint32_t)tid * sub, cover);
             const uint32_t my_hi = min(A + (uint32_t)(tid + 1) * sub, cover);
-            uint32_t pos = my_lo, cnt = 0, roff = kRegPad, last_dead = kNone;
+            uint32_t pos = my_lo, cnt = 0, last_dead = kNone;
             if (tid > 0 && my_lo < my_hi) {
                 // start `warm` bits early (or at the proven chunk start when that is closer)
                 pos = my_lo > rel_start + warm ? my_lo - warm : rel_start;
@@ -556,107 +556,67 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     pos = np;
                 }
             }
+            // (1b) decode my sub-block from `start` into my region, (2) verify: my first code
+            // word must begin where my predecessor's last one ended.  A thread that was not
+            // synchronised decodes its sub-block again from the proven position (codes that
+            // synchronise badly make that frequent; the loop is the same fast one), and since
+            // its end may move, the check repeats until nothing changes.
             uint32_t start = pos;  // first code word of mine (speculative unless tid == 0)
-            while (pos < my_hi) {
-                uint32_t e0, e1, e2, e3, p3;
-                const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
-                if (!((e0 | e1 | e2 | e3) & kFastFlags) && !(cnt & 3)) {
-                    // four plain table hits
-                    if (p3 < my_hi) {
-                        // ... that all start inside my sub-block: one 32-bit store
-                        pos = np;
-                        const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
-                        const uint32_t hi2 = __byte_perm(e2, e3, 0x0051);
-                        *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = __byte_perm(lo2, hi2, 0x5410);
-                        cnt += 4;
-                        continue;
-                    }
-                    // the fourth starts behind the boundary: at most three are mine
-                    reg[kRegPad + cnt++] = (uint8_t)(e0 >> 8);
-                    pos += e0 & 0xfu;
-                    if (pos < my_hi) {
-                        reg[kRegPad + cnt++] = (uint8_t)(e1 >> 8);
-                        pos += e1 & 0xfu;
-                    }
-                    if (pos < my_hi) {
-                        reg[kRegPad + cnt++] = (uint8_t)(e2 >> 8);
-                        pos += e2 & 0xfu;
-                    }
-                    break;
-                }
-                // irregular (special entry among the four, or an unaligned count): one exact step
-                const uint32_t at = pos;
-                uint32_t sy;
-                if (fast_step(sw, sm, pos, sy)) {
-                    reg[kRegPad + cnt] = (uint8_t)sy;
-                    cnt++;
-                } else {
-                    last_dead = at;
-                }
-            }
             uint32_t end = pos;
-            sm.sub_end[tid] = end;
-            cta_sync();
-
-            // (2) verification and (rare) sync-point fix-up
-            for (int round = 0; round < kFT; round++) {
-                const uint32_t want = (tid == 0 || (uint32_t)tid >= nact) ? start : sm.sub_end[tid - 1];
-                const bool redo = want != start;
-                cta_sync();
-                if (redo) {
-                    if (want >= my_hi) {
-                        cnt = 0;
-                        end = want;
-                        roff = kRegPad;
-                        last_dead = kNone;
-                    } else {
-                        const bool has_old = start < my_hi;
-                        uint32_t pa = want, pb = start, ca = 0, cb = 0, da = kNone;
-                        while (pa < my_hi && !(has_old && pa == pb)) {
-                            uint32_t sy;
-                            if (!has_old || pa < pb || pb >= my_hi) {
-                                const uint32_t at = pa;
-                                if (fast_step(sw, sm, pa, sy)) ca++; else da = at;
-                            } else {
-                                if (fast_step(sw, sm, pb, sy)) cb++;
+            bool walk = true;
+            for (int round = 0; round <= kFT; round++) {
+                if (walk) {
+                    pos = start;
+                    cnt = 0;
+                    last_dead = kNone;
+                    while (pos < my_hi) {
+                        uint32_t e0, e1, e2, e3, p3;
+                        const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
+                        if (!((e0 | e1 | e2 | e3) & kFastFlags) && !(cnt & 3)) {
+                            // four plain table hits
+                            if (p3 < my_hi) {
+                                // ... that all start inside my sub-block: one 32-bit store
+                                pos = np;
+                                const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
+                                const uint32_t hi2 = __byte_perm(e2, e3, 0x0051);
+                                *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = __byte_perm(lo2, hi2, 0x5410);
+                                cnt += 4;
+                                continue;
                             }
+                            // the fourth starts behind the boundary: at most three are mine
+                            reg[kRegPad + cnt++] = (uint8_t)(e0 >> 8);
+                            pos += e0 & 0xfu;
+                            if (pos < my_hi) {
+                                reg[kRegPad + cnt++] = (uint8_t)(e1 >> 8);
+                                pos += e1 & 0xfu;
+                            }
+                            if (pos < my_hi) {
+                                reg[kRegPad + cnt++] = (uint8_t)(e2 >> 8);
+                                pos += e2 & 0xfu;
+                            }
+                            break;
                         }
-                        uint32_t wr;  // region offset the new head is written at
-                        if (has_old && pa == pb && pa < my_hi) {
-                            // merged at pa: the old symbols from index cb on stay valid
-                            int32_t nroff = (int32_t)roff + (int32_t)cb - (int32_t)ca;
-                            if (nroff < 0) {
-                                // no room in front: slide the surviving tail to the right
-                                const uint32_t shift = (uint32_t)(-nroff);
-                                for (uint32_t q = cnt; q > cb; q--) reg[roff + q - 1 + shift] = reg[roff + q - 1];
-                                nroff = 0;
-                            }
-                            wr = (uint32_t)nroff;
-                            cnt = ca + (cnt - cb);
-                            last_dead = (last_dead != kNone && last_dead >= pa) ? last_dead : da;
+                        // irregular (special entry among the four, or an unaligned count): one exact step
+                        const uint32_t at = pos;
+                        uint32_t sy;
+                        if (fast_step(sw, sm, pos, sy)) {
+                            reg[kRegPad + cnt] = (uint8_t)sy;
+                            cnt++;
                         } else {
-                            wr = kRegPad;
-                            cnt = ca;
-                            end = pa;
-                            last_dead = da;
-                        }
-                        roff = wr;
-                        // rewrite the head: the first ca symbols of the new trajectory
-                        uint32_t p = want;
-                        for (uint32_t q = 0; q < ca;) {
-                            uint32_t sy;
-                            if (fast_step(sw, sm, p, sy)) {
-                                reg[wr + q] = (uint8_t)sy;
-                                q++;
-                            }
+                            last_dead = at;
                         }
                     }
-                    start = want;
+                    end = pos;
                     sm.sub_end[tid] = end;
                 }
+                cta_sync();
+                const uint32_t want = (tid == 0 || (uint32_t)tid >= nact) ? start : sm.sub_end[tid - 1];
+                walk = want != start;
+                start = want;
                 __syncwarp();
-                if (!__syncthreads_or(redo)) break;
+                if (!__syncthreads_or(walk)) break;
             }
+            const uint32_t roff = kRegPad;
 
             // (3) symbol-count scan
             const uint32_t incl = warp_incl_scan(cnt);
