@@ -17,9 +17,10 @@
 //                      and WRITES the symbols into a private shared-memory region (4 symbols per
 //                      32-bit store): no symbol is decoded twice
 //                  (2) verification: a thread's first code word must start where its
-//                      predecessor's last one ended.  The rare thread that did not synchronise
-//                      walks old and new trajectory in lockstep until they meet and rewrites only
-//                      the symbols in front of the meeting point
+//                      predecessor's last one ended.  A thread that did not synchronise decodes
+//                      its sub-block again from the proven position; rounds repeat until nothing
+//                      moves (codes that never re-synchronise, e.g. p(k) = 2^-(k+1), degrade to a
+//                      sequential ripple over the threads of a chunk: slow, never wrong)
 //                  (3) symbol-count scan -> output position of every region
 //                  (4) regions compacted into a linear shared buffer (aliasing the stage) and
 //                      copied out with coalesced 16-byte stores.
@@ -254,6 +255,7 @@ struct FastSmem {
     uint32_t long_code[kLongMax];  // left-aligned code words longer than the table reach, ascending
     uint16_t long_ent[kLongMax];   // length << 8 | symbol
     uint32_t nlong;
+    unsigned long long next_j;
     uint32_t warp_tot[kFT / 32];
     uint32_t redo;
     uint32_t fin_found;
@@ -387,8 +389,13 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
     uint8_t *reg = regions + tid * kRegStride;
     const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
-    for (uint64_t j = blockIdx.x; j < ncand; j += gridDim.x) {
+    for (;;) {
+        // blocks are handed out dynamically (result[11] is the work counter): block costs differ
         cta_sync();
+        if (tid == 0) sm.next_j = atomicAdd(reinterpret_cast<unsigned long long *>(&a.result[11]), 1ull);
+        cta_sync();
+        const uint64_t j = sm.next_j;
+        if (j >= ncand) break;
         const uint32_t meta = a.meta[2 * j];
         const uint32_t nlong = a.meta[2 * j + 1];
         const uint64_t off = a.cand[j];
@@ -572,14 +579,23 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     while (pos < my_hi) {
                         uint32_t e0, e1, e2, e3, p3;
                         const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
-                        if (!((e0 | e1 | e2 | e3) & kFastFlags) && !(cnt & 3)) {
+                        if (!((e0 | e1 | e2 | e3) & kFastFlags)) {
                             // four plain table hits
                             if (p3 < my_hi) {
-                                // ... that all start inside my sub-block: one 32-bit store
+                                // ... that all start inside my sub-block: one 32-bit store (four
+                                // byte stores while a long code word has left the count unaligned)
                                 pos = np;
                                 const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
                                 const uint32_t hi2 = __byte_perm(e2, e3, 0x0051);
-                                *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = __byte_perm(lo2, hi2, 0x5410);
+                                const uint32_t four = __byte_perm(lo2, hi2, 0x5410);
+                                if (!(cnt & 3)) {
+                                    *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = four;
+                                } else {
+                                    reg[kRegPad + cnt] = (uint8_t)four;
+                                    reg[kRegPad + cnt + 1] = (uint8_t)(four >> 8);
+                                    reg[kRegPad + cnt + 2] = (uint8_t)(four >> 16);
+                                    reg[kRegPad + cnt + 3] = (uint8_t)(four >> 24);
+                                }
                                 cnt += 4;
                                 continue;
                             }
@@ -596,7 +612,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                             }
                             break;
                         }
-                        // irregular (special entry among the four, or an unaligned count): one exact step
+                        // irregular (special entry among the four): one exact step
                         const uint32_t at = pos;
                         uint32_t sy;
                         if (fast_step(sw, sm, pos, sy)) {

@@ -66,6 +66,7 @@ struct DecArgs {
                            // [8] sparse-mode slot overflow (rerun with the two-pass scan)
                            // [9] largest block extent (header + payload bytes) seen
                            // [10] blocks the fast lane left to k_decode_slow
+                           // [11] work counter of k_decode (next candidate to hand out)
 };
 
 // ------------------------------------------------------------------------------------------
