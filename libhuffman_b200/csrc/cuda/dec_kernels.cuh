@@ -156,16 +156,23 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
             // bytes o0+11 .. o0+26 decide the pre-filter
             if (fast) {
                 const uint32_t d[8] = {v[u].x, v[u].y, v[u].z, v[u].w, n0, n1, n2, 0u};
-                uint32_t pre = 0;
+                // tree[0] high byte (offsets 11+4j .. 14+4j) must be 0x01 and the tree_len high
+                // byte (offsets 9+4j .. 12+4j) at most 0x04: 1 in 13000 random offsets, so the
+                // per-offset bit mask is only assembled when some byte lane survived
+                uint32_t eq[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    // tree[0] high byte (offsets 11+4j .. 14+4j) must be 0x01 and the tree_len
-                    // high byte (offsets 9+4j .. 12+4j) at most 0x04: 1 in 13000 random offsets
                     const uint32_t w11 = __funnelshift_r(d[2 + j], d[3 + j], 24);
                     const uint32_t w9 = __funnelshift_r(d[2 + j], d[3 + j], 8);
-                    const uint32_t eq = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
-                    pre |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u))
-                           << (4 * j);
+                    eq[j] = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
+                }
+                uint32_t pre = 0;
+                if (eq[0] | eq[1] | eq[2] | eq[3]) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        pre |= ((eq[j] & 1u) | ((eq[j] >> 7) & 2u) | ((eq[j] >> 14) & 4u) | ((eq[j] >> 21) & 8u))
+                               << (4 * j);
+                    }
                 }
                 while (pre) {
                     const int i = __ffs(pre) - 1;
