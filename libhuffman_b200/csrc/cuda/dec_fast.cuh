@@ -65,6 +65,8 @@ constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
 
+constexpr int kRespecMin = 2;             // threads still failing after one repair round: a ripple, re-speculate
+constexpr int kRespecStarts = 16;         // warm-up start offsets tried for the alternate trajectory
 constexpr int kTreeWin = 520;             // serialised tree elements staged per lane at a time
 constexpr int kTreeHdrStride = 1052;      // staged bytes per candidate (263 words, odd)
 constexpr int kTreeDyn = 32 * kTreeHdrStride;
@@ -256,6 +258,9 @@ struct FastSmem {
     uint16_t long_ent[kLongMax];   // length << 8 | symbol
     uint32_t nlong;
     unsigned long long next_j;
+    uint32_t c_start[2][kFT];      // re-speculation: first code word of the primary / alternate
+    uint32_t c_end[2][kFT];        // trajectory of every sub-block and where it leaves it
+    uint32_t pred[kFT];            // predicted true start of every sub-block
     uint32_t warp_tot[kFT / 32];
     uint32_t redo;
     uint32_t fin_found;
@@ -546,23 +551,28 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             const uint32_t my_lo = tid == 0 ? rel_start : min(A + (uint32_t)tid * sub, cover);
             const uint32_t my_hi = min(A + (uint32_t)(tid + 1) * sub, cover);
             uint32_t pos = my_lo, cnt = 0, last_dead = kNone;
-            if (tid > 0 && my_lo < my_hi) {
-                // start `warm` bits early (or at the proven chunk start when that is closer)
-                pos = my_lo > rel_start + warm ? my_lo - warm : rel_start;
-                // four steps at a time while all four start in front of my sub-block
-                while (pos < my_lo) {
+            // blind walk (every entry advances by its length field, specials by one bit) from
+            // `from` to the first position >= limit
+            auto blind_to = [&](uint32_t from, uint32_t limit) -> uint32_t {
+                uint32_t p = from;
+                // four steps at a time while all four start in front of the limit
+                while (p < limit) {
                     uint32_t e0, e1, e2, e3, p3;
-                    const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
-                    if (p3 >= my_lo) {
-                        // the fourth starts behind the boundary: take the steps in front of it
-                        if (pos < my_lo) pos += e0 & 0xfu;
-                        if (pos < my_lo) pos += e1 & 0xfu;
-                        if (pos < my_lo) pos += e2 & 0xfu;
+                    const uint32_t np = fast_look4(sw, sm.lut, p, e0, e1, e2, e3, p3);
+                    if (p3 >= limit) {
+                        // the fourth starts behind the limit: take the steps in front of it
+                        if (p < limit) p += e0 & 0xfu;
+                        if (p < limit) p += e1 & 0xfu;
+                        if (p < limit) p += e2 & 0xfu;
                         break;
                     }
-                    pos = np;
+                    p = np;
                 }
-            }
+                return p;
+            };
+            // start `warm` bits early (or at the proven chunk start when that is closer)
+            const uint32_t warm_from = my_lo > rel_start + warm ? my_lo - warm : rel_start;
+            if (tid > 0 && my_lo < my_hi) pos = blind_to(warm_from, my_lo);
             // (1b) decode my sub-block from `start` into my region, (2) verify: my first code
             // word must begin where my predecessor's last one ended.  A thread that was not
             // synchronised decodes its sub-block again from the proven position (codes that
@@ -628,9 +638,55 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 cta_sync();
                 const uint32_t want = (tid == 0 || (uint32_t)tid >= nact) ? start : sm.sub_end[tid - 1];
                 walk = want != start;
+                const uint32_t had = start;  // what my region was decoded from
                 start = want;
                 __syncwarp();
-                if (!__syncthreads_or(walk)) break;
+                const int nfail = __syncthreads_count(walk);
+                if (nfail == 0) break;
+                if (round == 1 && nfail >= kRespecMin) {
+                    // Re-speculation.  Isolated failures are gone after one repair round; threads
+                    // that still fail do so because a repaired predecessor ended elsewhere: the
+                    // code synchronises badly (e.g. p(k) = 2^-(k+1) keeps a shifted parse shifted
+                    // for ever) and repairs would ripple through the chunk one round each.  Every
+                    // thread looks for a second trajectory class (blind walks from 16 adjacent
+                    // start bits reach every trajectory that crosses the warm-up zone), follows
+                    // it through its sub-block, and one thread chains the classes from the proven
+                    // chunk start.  The result only PREDICTS starts: the verification rounds
+                    // below still decide, so a wrong prediction costs time, never correctness.
+                    uint32_t alt = kNone, alt_end = kNone;
+                    if (tid > 0 && my_lo < my_hi) {
+                        for (uint32_t k = 1; k < (uint32_t)kRespecStarts && alt == kNone; k++) {
+                            if (warm_from + k >= my_lo) break;
+                            const uint32_t b = blind_to(warm_from + k, my_lo);
+                            if (b != had) alt = b;
+                        }
+                        if (alt != kNone) alt_end = blind_to(alt, my_hi);
+                    }
+                    sm.c_start[0][tid] = had;
+                    sm.c_end[0][tid] = end;
+                    sm.c_start[1][tid] = alt;
+                    sm.c_end[1][tid] = alt_end;
+                    cta_sync();
+                    if (tid == 0) {
+                        uint32_t cur = sm.c_end[0][0];  // thread 0 decoded from the proven start
+                        sm.pred[0] = sm.c_start[0][0];
+                        for (uint32_t t = 1; t < nact; t++) {
+                            sm.pred[t] = cur;
+                            if (cur == sm.c_start[0][t]) {
+                                cur = sm.c_end[0][t];
+                            } else if (cur == sm.c_start[1][t]) {
+                                cur = sm.c_end[1][t];
+                            } else {
+                                cur = sm.c_end[0][t];  // unknown class: guess, verification repairs
+                            }
+                        }
+                    }
+                    cta_sync();
+                    if ((uint32_t)tid < nact) {
+                        start = sm.pred[tid];
+                        walk = start != had;
+                    }
+                }
             }
             const uint32_t roff = kRegPad;
 

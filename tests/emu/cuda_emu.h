@@ -247,6 +247,19 @@ inline int __syncthreads_or(int pred)
     return r;
 }
 
+inline int __syncthreads_count(int pred)
+{
+    static unsigned acc = 0, result = 0;  // CTAs run one after another
+    if (pred) acc++;
+    __syncthreads();
+    result = acc;
+    __syncthreads();
+    const int r = (int)result;
+    acc = 0;
+    __syncthreads();
+    return r;
+}
+
 inline void __syncwarp(unsigned = 0xffffffffu)
 {
     hufemu::Warp *w = hufemu::cta()->cur->warp;
