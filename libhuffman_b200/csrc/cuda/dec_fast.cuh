@@ -353,30 +353,40 @@ __device__ __forceinline__ void cta_sync()
     __syncthreads();
 }
 
-// Copy n bytes between two shared-memory locations of arbitrary alignment, word-wise.
+// Copy n bytes between two shared-memory locations of arbitrary alignment: up to three bytes to
+// align the destination, then whole words assembled with one funnel shift each (four per
+// iteration), then up to three bytes.
 __device__ __forceinline__ void smem_copy(uint8_t *dst, const uint8_t *src, uint32_t n)
 {
-    while (n && (reinterpret_cast<uintptr_t>(dst) & 3)) {
-        *dst++ = *src++;
-        n--;
+    const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+    if (head > 0) dst[0] = src[0];
+    if (head > 1) dst[1] = src[1];
+    if (head > 2) dst[2] = src[2];
+    // source bytes head.. : word k = funnel(s[k], s[k + 1], sh)
+    const uintptr_t sp = reinterpret_cast<uintptr_t>(src + head);
+    const uint32_t sh = (uint32_t)(sp & 3) * 8;
+    const uint32_t *s = reinterpret_cast<const uint32_t *>(sp & ~uintptr_t(3));
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t prev = s[0];
+    uint32_t k = 0;
+    for (; k + 4 <= nw; k += 4) {
+        const uint32_t a1 = s[k + 1], a2 = s[k + 2], a3 = s[k + 3], a4 = s[k + 4];
+        d[k] = __funnelshift_r(prev, a1, sh);
+        d[k + 1] = __funnelshift_r(a1, a2, sh);
+        d[k + 2] = __funnelshift_r(a2, a3, sh);
+        d[k + 3] = __funnelshift_r(a3, a4, sh);
+        prev = a4;
     }
-    if (n >= 4) {
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
-        const uint32_t *s = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
-        uint32_t prev = *s;
-        do {
-            const uint32_t next = *++s;
-            *reinterpret_cast<uint32_t *>(dst) = __funnelshift_r(prev, next, sh);
-            prev = next;
-            dst += 4;
-            src += 4;
-            n -= 4;
-        } while (n >= 4);
+    for (; k < nw; k++) {
+        const uint32_t a1 = s[k + 1];
+        d[k] = __funnelshift_r(prev, a1, sh);
+        prev = a1;
     }
-    while (n) {
-        *dst++ = *src++;
-        n--;
-    }
+    const uint32_t done = head + 4 * nw;
+    if (done < n) dst[done] = src[done];
+    if (done + 1 < n) dst[done + 1] = src[done + 1];
+    if (done + 2 < n) dst[done + 2] = src[done + 2];
 }
 
 __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
