@@ -168,3 +168,26 @@ def test_emu_fast_lane_takes_encoder_shaped_blocks(emu, harness):
     data = bytes(range(256)) * 3
     rc, got, slow = _lanes(emu, harness.oracle_encode(data, 0), len(data))
     assert rc == 5 and slow == 1
+
+
+def test_emu_corrupted_large_block_error_parity(emu, harness):
+    """Same as the GPU lane's large-block corruption test, a few cases: damaged 64 KiB blocks must
+    leave the fast lane and get the oracle's error code / bytes from the general lane."""
+    rng = np.random.default_rng(23)
+    data = datagen.zipf(2 * 65536 + 77, 255, seed=5)
+    base = harness.oracle_encode(data, 65536)
+    for it in range(6):
+        s = bytearray(base)
+        if it % 3 == 0:
+            s = s[: int(rng.integers(len(s) // 2, len(s)))]
+        elif it % 3 == 1:
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            pos = int(rng.integers(0, len(s) - 64))
+            s[pos:pos + 64] = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        s = bytes(s)
+        rc_o, out_o, _ = harness.oracle_decode(s)
+        rc, got = emu.decode(s)
+        assert rc == rc_o, (it, rc, rc_o)
+        if rc == 0:
+            assert got == out_o, it

@@ -131,6 +131,37 @@ def test_corrupted_streams_error_parity(lib, harness):
             assert got == out_o
 
 
+@pytest.mark.parametrize("shape", ["zipf255", "geometric"])
+def test_corrupted_large_blocks_error_parity(lib, harness, shape):
+    """Bit flips, overwrites and truncation in streams of 64 KiB blocks (several chunks per block
+    in the fast lane, re-speculation for the geometric shape): the error code, and for successful
+    decodes the bytes, must be the oracle's; the fast lane has to hand every damaged block to the
+    general lane.  A flip inside a payload usually still decodes (to different bytes)."""
+    rng = np.random.default_rng(23)
+    n = 5 * 65536 + 1234
+    data = datagen.zipf(n, 255, seed=5) if shape == "zipf255" else datagen.geometric(n, seed=5)
+    base = harness.oracle_encode(data, 65536)
+    for it in range(40):
+        s = bytearray(base)
+        kind = it % 4
+        if kind == 0:
+            s = s[: int(rng.integers(len(s) // 2, len(s)))]
+        elif kind == 1:
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:
+            pos = int(rng.integers(0, len(s) - 64))
+            s[pos:pos + 64] = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        else:
+            pos = int(rng.integers(0, len(s) - 4096))
+            s[pos:pos + 4096] = bytes(4096)
+        s = bytes(s)
+        rc_o, out_o, _ = harness.oracle_decode(s)
+        rc, got = lib.decode(s)
+        assert rc == rc_o, (it, kind, rc, rc_o)
+        if rc == 0:
+            assert got == out_o, (it, kind)
+
+
 def test_short_reader_and_length_semantics(lib, harness):
     data = datagen.english_text(1000, seed=2)
     rc, got = lib.encode(data[:700], 300, length=1000)
