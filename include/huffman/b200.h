@@ -86,6 +86,14 @@ huf_error_t huf_b200_encode_block_offsets(huf_b200_ctx_t *ctx, const uint64_t **
 huf_error_t huf_b200_decode_async(huf_b200_ctx_t *ctx, const void *d_in, uint64_t avail,
                                   uint64_t length, void *d_out, uint64_t out_capacity,
                                   void *stream);
+/* Optional block index for the NEXT huf_b200_decode_async call on this context: d_offsets is a
+ * device array of `nblocks` ascending byte offsets of block headers in d_in (entry 0 = 0), e.g.
+ * what huf_b200_encode_block_offsets returned for this very stream.  With it the decoder skips
+ * the speculative header scan (the stream format has no index, src/encoder.c:325-342).  The
+ * index never changes results: every block is still proven by the chain check, and a wrong
+ * index only costs a rescan.  The array must stay valid until decode_finish. */
+huf_error_t huf_b200_decode_hint_offsets(huf_b200_ctx_t *ctx, const uint64_t *d_offsets,
+                                         uint64_t nblocks);
 /* Wait; *out_len = decoded bytes valid in d_out, *consumed = compressed bytes consumed.
  * Returns the reference's error code for the first failing block (earlier blocks' output is
  * valid), HUF_ERROR_READ_WRITE when a block runs past `avail`. */

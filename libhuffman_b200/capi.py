@@ -175,6 +175,7 @@ class B200Lib(HuffmanCLib):
         d.huf_b200_decode_plan.argtypes = [vp, vp, u64, u64, C.POINTER(u64), C.POINTER(u64), vp]
         d.huf_b200_last_launch_count.restype = u64
         d.huf_b200_last_launch_count.argtypes = [vp]
+        d.huf_b200_decode_hint_offsets.argtypes = [vp, vp, u64]
         d.huf_b200_last_slow_blocks.restype = u64
         d.huf_b200_last_slow_blocks.argtypes = [vp]
         d.huf_b200_kernel_times.argtypes = [vp, C.c_char_p, u64]
@@ -236,6 +237,11 @@ class DeviceCodec:
                      stream: int = 0) -> None:
         self.lib.check(self.lib.dll.huf_b200_decode_async(self.ctx, d_in, avail, length, d_out,
                                                           out_cap, stream), "huf_b200_decode_async")
+
+    def decode_hint_offsets(self, d_offsets: int, nblocks: int) -> None:
+        """Block index (device u64 array) for the next decode_async: skips the header scan."""
+        self.lib.check(self.lib.dll.huf_b200_decode_hint_offsets(self.ctx, d_offsets, nblocks),
+                       "huf_b200_decode_hint_offsets")
 
     def decode_finish(self) -> tuple[int, int, int]:
         """Returns (huf_error_t, decoded bytes, consumed bytes)."""

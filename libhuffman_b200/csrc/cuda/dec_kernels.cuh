@@ -231,6 +231,30 @@ __global__ void k_compact(DecArgs a)
     }
 }
 
+// Candidate list from a caller-supplied block index (the offset array an encoder returns,
+// huf_b200_encode_block_offsets) instead of the header scan.  The entries are only hints: the
+// chain validation still proves every block, and a wrong index just costs a restart with the
+// scan.  Offsets must ascend; those at or behind the consumable range are dropped.
+__global__ void k_hint(DecArgs a, const uint64_t *__restrict__ hint, uint64_t n)
+{
+    const uint64_t lim = a.length < a.avail ? a.length : a.avail;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i < a.max_cand) {
+        const uint64_t off = i == 0 ? a.first : hint[i];  // the proven start is always block 0
+        a.cand[i] = off < lim ? off : lim;
+    }
+    if (i == 0) {
+        // count = entries in front of `lim` (binary search over the ascending array)
+        uint64_t lo = 0, hi = n < a.max_cand ? n : a.max_cand;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if ((mid == 0 ? a.first : hint[mid]) < lim) lo = mid + 1; else hi = mid;
+        }
+        a.result[0] = lo ? lo : 1;
+        a.result[6] = lo ? lo : 1;
+    }
+}
+
 // chunk counts -> exclusive offsets, total candidate count -> result[0].  One CTA.
 __global__ void __launch_bounds__(kScanThreads) k_scan_chunks(DecArgs a)
 {

@@ -121,6 +121,8 @@ struct huf_b200_ctx {
     bool dec_pending = false;
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
+    const uint64_t *hint_off = nullptr;  // optional block index for the next decode (device pointer)
+    uint64_t hint_n = 0;
     uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode_slow
     bool slow_ready = false;        // k_decode_slow attribute set
     bool fast_ready = false;        // k_decode attributes set
@@ -497,6 +499,8 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     a.nchunks = (span + kFindChunk - 1) / kFindChunk;
     if (!a.nchunks) a.nchunks = 1;
     uint64_t max_cand = max_cand_hint ? max_cand_hint : span / 256 + 1024;
+    const bool hinted = c->hint_off && c->hint_n && first == 0 && !plan_only;
+    if (hinted && max_cand < c->hint_n + 16) max_cand = c->hint_n + 16;
     a.max_cand = max_cand;
 
     size_t need = 0;
@@ -525,7 +529,12 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
 
     CU_TRY(cudaMemsetAsync(c->d_result, 0, 16 * sizeof(uint64_t), st));
     const unsigned find_grid = (unsigned)((a.nchunks + kFindWarps - 1) / kFindWarps);
-    if (c->dec_dense) {
+    if (hinted) {
+        // block index supplied by the caller: no header scan in this pass
+        CTX_LAUNCH(c, k_hint, (unsigned)((c->hint_n + 255) / 256), 256, 0, st, a, c->hint_off, c->hint_n);
+        c->hint_off = nullptr;  // a restart after a broken chain scans
+        c->hint_n = 0;
+    } else if (c->dec_dense) {
         CTX_LAUNCH(c, k_find<0>, find_grid, kFindWarps * 32, 0, st, a);
         CTX_LAUNCH(c, k_scan_chunks, 1, kScanThreads, 0, st, a);
         CTX_LAUNCH(c, k_find<1>, find_grid, kFindWarps * 32, 0, st, a);
@@ -607,6 +616,14 @@ huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     a.out_cap = out_capacity;
     if (!length) return HUF_ERROR_SUCCESS;  // src/decoder.c:218: nothing to consume
     return dec_enqueue(c, 0, 0, false, 0);
+}
+
+huf_error_t huf_b200_decode_hint_offsets(huf_b200_ctx_t *c, const uint64_t *d_offsets, uint64_t nblocks)
+{
+    if (!c) return HUF_ERROR_INVALID_ARGUMENT;
+    c->hint_off = nblocks ? d_offsets : nullptr;
+    c->hint_n = d_offsets ? nblocks : 0;
+    return HUF_ERROR_SUCCESS;
 }
 
 huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_t *consumed)

@@ -191,3 +191,44 @@ def test_emu_corrupted_large_block_error_parity(emu, harness):
         assert rc == rc_o, (it, rc, rc_o)
         if rc == 0:
             assert got == out_o, it
+
+
+def test_emu_decode_with_block_index_hint(emu, harness):
+    """the encoder's block-offset array as a decode-side index.  With it the
+    header scan is skipped; a wrong index must not change the result (chain check + rescan)."""
+    data = datagen.zipf(50000, 200, seed=12)
+    bs = 4096
+    want = harness.oracle_encode(data, bs)
+    enc = DeviceCodec(emu)
+    dec = DeviceCodec(emu)
+    try:
+        src = C.create_string_buffer(data, len(data))
+        cap = enc.encode_bound(len(data), bs)
+        comp = C.create_string_buffer(cap + 16)
+        enc.encode_async(C.addressof(src), len(data), bs, C.addressof(comp), cap)
+        n = enc.encode_finish()
+        assert comp.raw[:n] == want
+        ptr, nb = enc.block_offsets()
+        offs = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), (nb + 1,)).copy()
+        out = C.create_string_buffer(len(data) + 64)
+        # the encoder's own index: no k_find launch
+        dec.decode_hint_offsets(ptr, nb)
+        dec.decode_async(C.addressof(comp), n, n, C.addressof(out), len(data) + 64)
+        hinted_launches = dec.launches()
+        assert dec.decode_finish() == (0, len(data), n) and out.raw[:len(data)] == data
+        # without the hint one more kernel family runs (the scan)
+        dec.decode_async(C.addressof(comp), n, n, C.addressof(out), len(data) + 64)
+        assert dec.launches() > hinted_launches
+        assert dec.decode_finish() == (0, len(data), n)
+        # a damaged index (one offset off by 3, one block missing) costs a rescan, not correctness
+        bad = offs[:nb].copy()
+        bad[3] += 3
+        bad = np.delete(bad, 7)
+        badbuf = (C.c_uint64 * len(bad))(*bad.tolist())
+        out2 = C.create_string_buffer(len(data) + 64)
+        dec.decode_hint_offsets(C.addressof(badbuf), len(bad))
+        dec.decode_async(C.addressof(comp), n, n, C.addressof(out2), len(data) + 64)
+        assert dec.decode_finish() == (0, len(data), n) and out2.raw[:len(data)] == data
+    finally:
+        enc.close()
+        dec.close()

@@ -306,3 +306,40 @@ def test_shape_blocksize_matrix(lib, harness, shape, bs):
     assert rc == 0 and got == want
     rc, back = lib.decode(want)
     assert rc == 0 and back == data
+
+
+def test_decode_with_block_index_hint(lib, torch_cuda, codec):
+    """SURVEY.md §8(f)4 on the device: the encoder's offset array as decode-side index (no header
+    scan), and a damaged index that must not change the result."""
+    torch = torch_cuda
+    n, bs = 8 << 20, 65536
+    x = datagen.zipf_torch(n, torch.device("cuda", 0), 255, seed=9)
+    cap = codec.encode_bound(n, bs)
+    comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    codec.encode_async(x.data_ptr(), n, bs, comp.data_ptr(), cap, st)
+    c = codec.encode_finish()
+    ptr, nb = codec.block_offsets()
+    assert nb == n // bs
+    dec = DeviceCodec(lib, 0)
+    try:
+        back = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+        dec.decode_hint_offsets(ptr, nb)
+        dec.decode_async(comp.data_ptr(), c, c, back.data_ptr(), n + 64, st)
+        hinted = dec.launches()
+        assert dec.decode_finish() == (0, n, c) and torch.equal(back[:n], x)
+        dec.decode_async(comp.data_ptr(), c, c, back.data_ptr(), n + 64, st)
+        assert dec.launches() > hinted
+        assert dec.decode_finish() == (0, n, c)
+        # copy the device offsets, damage them, feed them back
+        host = np.zeros(nb, dtype=np.uint64)
+        lib.check(lib.dll.huf_b200_copy_d2h(host.ctypes.data, ptr, 8 * nb), "copy_d2h")
+        host[5] += 7
+        host = np.delete(host, 11)
+        bad = torch.from_numpy(host.astype(np.int64)).cuda()
+        back.zero_()
+        dec.decode_hint_offsets(bad.data_ptr(), len(host))
+        dec.decode_async(comp.data_ptr(), c, c, back.data_ptr(), n + 64, st)
+        assert dec.decode_finish() == (0, n, c) and torch.equal(back[:n], x)
+    finally:
+        dec.close()
