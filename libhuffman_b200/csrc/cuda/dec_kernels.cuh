@@ -7,12 +7,16 @@
 //                      4n+1, tree[0] = 255+n, plausible orig_len), two passes: count per chunk,
 //                      then ordered emit.  Offset `first` is always a candidate (true start).
 //   K4b k_gather/scan  orig_len of each candidate -> exclusive scan -> output offsets.
-//   K5  k_decode       one CTA per candidate block: header parse + tree_len bound check
-//                      (src/decoder.c:220-239), tree -> node arrays + 12-bit lookup table in
-//                      shared memory (replaces huf_tree_deserialize, src/tree.c:138-227),
-//                      self-synchronising speculative sub-block decode with a sync-point
-//                      fix-up loop and a symbol-count scan (replaces __huf_decode_block,
-//                      src/decoder.c:34-96), coalesced output from a shared staging buffer.
+//   K4d k_tree         (dec_fast.cuh) lane-per-candidate tree walk for encoder-shaped trees.
+//   K5  k_decode       (dec_fast.cuh) the fast lane: chunked warm-up / verify decode of clean
+//                      blocks, symbols written once.
+//   K5s k_decode_slow  the general lane, for every block the fast lane declines: header parse +
+//                      tree_len bound check (src/decoder.c:220-239), tree -> node arrays +
+//                      12-bit lookup table in shared memory with the whole acceptance grammar
+//                      (replaces huf_tree_deserialize, src/tree.c:138-227), self-synchronising
+//                      speculative sub-block decode with a sync-point fix-up loop and a
+//                      symbol-count scan (replaces __huf_decode_block, src/decoder.c:34-96),
+//                      the reference's error codes.
 //   K4c k_verify       chain validation: end(j) must equal candidate(j+1); first violation or
 //                      error ends the proven chain.  The host restarts after it if needed, so
 //                      the result is exact; speculation only affects speed.

@@ -9,13 +9,17 @@
 //                       Replaces huf_tree_from_histogram (src/tree.c:292-427),
 //                       __huf_create_char_coding (src/encoder.c:40-81) + huf_node_to_string
 //                       (src/tree.c:12-47) and huf_tree_serialize (src/tree.c:233-289).
+//                       Used with 64-bit keys for blocks above 4 MiB only; ordinary blocks go
+//                       through the three kernels of enc_build.cuh (sort / lane-per-block merge
+//                       / codes).
 //       k_scan_sizes    exclusive scan of block byte sizes -> block offsets in the stream.
-//   K3  k_pack          one warp per segment: code lookup, warp scan of code lengths,
+//   K3w k_pack_wide     one warp per segment: code lookup, warp scan of code lengths,
 //                       funnel-shift bit packing into a shared staging window, coalesced
 //                       32-bit big-endian word stores; also emits the block header.
 //                       Replaces the header writes (src/encoder.c:325-342) and
 //                       __huf_encode_block + huf_bit_write (src/encoder.c:85-131,
-//                       src/bufio.c:18-32).
+//                       src/bufio.c:18-32).  Takes the blocks with a code word above 16 bits;
+//                       all others go through k_pack in enc_pack.cuh.
 //
 // Data layout in HBM (all sizes for nblocks blocks, nspb segments per block):
 //   seg_hist   u16 [nblocks*nspb][256]    written by K1, read by K2
