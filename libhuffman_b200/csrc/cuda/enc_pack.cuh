@@ -1,9 +1,10 @@
 // enc_pack.cuh — K3 fast lane: bit packing for blocks whose longest code word is <= 16 bits
 // (every block of ordinary data; deeper trees take k_pack_wide in enc_kernels.cuh).
 //
-// One warp per segment, 16 symbols per lane and iteration.  Code words are looked up as
-// {left-aligned code, length} pairs with one 8-byte shared-memory load, two neighbours are
-// concatenated in registers (<= 32 bits), the lane's bit offset comes from a warp scan of the
+// One warp per segment, 16 symbols per lane and iteration.  Code words are looked up with one
+// 4-byte shared-memory load (left-aligned code in the top half, length below: the kernel is
+// bound by shared-memory wavefronts, so the table entry is kept to one bank word), two
+// neighbours are concatenated in registers (<= 32 bits), the lane's bit offset comes from a warp scan of the
 // lengths, and finished 32-bit words are OR-ed into a zeroed staging window with shared-memory
 // atomics, so lanes that share a word need no hand-over protocol.  Whole words leave as
 // coalesced big-endian 32-bit stores; only the first and last bytes of a segment, which share a
@@ -22,7 +23,7 @@ constexpr uint32_t kPackFastMaxLen = 16;
 constexpr int kPackStageWords = 288;  // 16 symbols x 16 bits x 32 lanes = 256 words + kept line, padded
 
 struct PackFastSmem {
-    uint2 table[kEncWarps][256];               // {code << (32 - len), len}
+    uint32_t table[kEncWarps][256];            // code << (32 - len) in the top 16 bits | len
     __align__(16) uint32_t stage[kEncWarps][kPackStageWords];
 };
 
@@ -88,14 +89,11 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         }
     }
 
-    // per-warp copy of the code table, split into {code, length}
-    uint2 *tab = sm.table[w];
+    // per-warp copy of the code table (codes are at most 16 bits here: the low half holds the length)
+    uint32_t *tab = sm.table[w];
     {
         const uint32_t *src = a.blk_table + bl * 512;
-        for (int i = lane; i < 256; i += 32) {
-            const uint32_t e = src[i];
-            tab[i] = make_uint2(e & ~31u, e & 31u);
-        }
+        for (int i = lane; i < 256; i += 32) tab[i] = src[i];
     }
     uint32_t *stage = sm.stage[w];
     for (int i = lane; i < kPackStageWords / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
@@ -121,9 +119,10 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
             uint64_t idx = soff;
             while (got < rb) {
                 idx--;
-                const uint2 e = tab[blk_in[idx]];
-                val |= (e.x >> (32 - e.y)) << got;
-                got += e.y;
+                const uint32_t e = tab[blk_in[idx]];
+                const uint32_t l = e & 31u;
+                val |= ((e & 0xffff0000u) >> (32 - l)) << got;
+                got += l;
             }
             val &= (1u << rb) - 1u;
             stage[q >> 5] = val << (32 - (q & 31));  // rb != 0 implies q & 31 != 0
@@ -132,6 +131,8 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     __syncwarp();
 
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    uint4 pre = make_uint4(0, 0, 0, 0);  // software pipeline: the lane's next 16 input bytes
+    if (aligned && slen >= 512) pre = ld_stream_u4(p + lane * 16);
     // One iteration = 16 symbols per lane.  FULL: every lane has 16 symbols and the input is
     // 16-byte aligned (all iterations but the last of a segment).
     auto iteration = [&](auto full_tag, uint32_t base) {
@@ -140,8 +141,9 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         uint32_t sym[4] = {0, 0, 0, 0};
         uint32_t nvalid = 16;
         if (FULL) {
-            const uint4 v = ld_stream_u4(p + my0);
-            sym[0] = v.x; sym[1] = v.y; sym[2] = v.z; sym[3] = v.w;
+            // this iteration's bytes were requested one iteration ago; request the next ones now
+            sym[0] = pre.x; sym[1] = pre.y; sym[2] = pre.z; sym[3] = pre.w;
+            if (base + 1024 <= slen) pre = ld_stream_u4(p + my0 + 512);
         } else {
             nvalid = my0 < slen ? min(16u, slen - my0) : 0u;
 #pragma unroll
@@ -155,13 +157,14 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         for (int j = 0; j < 8; j++) {
             const uint32_t s0 = __byte_perm(sym[j >> 1], 0, 0x4440 + 2 * (j & 1));
             const uint32_t s1 = __byte_perm(sym[j >> 1], 0, 0x4441 + 2 * (j & 1));
-            uint2 e0 = tab[s0], e1 = tab[s1];
+            uint32_t e0 = tab[s0], e1 = tab[s1];
             if (!FULL) {
-                if ((uint32_t)(2 * j) >= nvalid) e0 = make_uint2(0, 0);
-                if ((uint32_t)(2 * j + 1) >= nvalid) e1 = make_uint2(0, 0);
+                if ((uint32_t)(2 * j) >= nvalid) e0 = 0;
+                if ((uint32_t)(2 * j + 1) >= nvalid) e1 = 0;
             }
-            t[j] = e0.x | (e1.x >> e0.y);
-            lp[j] = e0.y + e1.y;
+            const uint32_t l0 = e0 & 31u;
+            t[j] = (e0 & 0xffff0000u) | ((e1 & 0xffff0000u) >> l0);
+            lp[j] = l0 + (e1 & 31u);
             total_l += lp[j];
         }
         const uint32_t incl = warp_incl_scan(total_l);
