@@ -104,4 +104,45 @@ __device__ __forceinline__ T warp_incl_scan(T v)
     return v;
 }
 
+// Per-thread pieces of the single-CTA scans: a thread owns the contiguous range [lo, hi).
+// Eight loads are issued before any use, so a range costs a few memory latencies, not one per item.
+template <typename T>
+__device__ __forceinline__ uint64_t range_sum(const T *in, uint64_t lo, uint64_t hi)
+{
+    uint64_t sum = 0;
+    uint64_t i = lo;
+    for (; i + 8 <= hi; i += 8) {
+        T v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = in[i + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) sum += v[q];
+    }
+    for (; i < hi; i++) sum += in[i];
+    return sum;
+}
+
+// out[i] = run + sum(in[lo..i)) for i in [lo, hi); returns run + sum(in[lo..hi)).
+template <typename T>
+__device__ __forceinline__ uint64_t range_excl_scan(const T *in, uint64_t *out, uint64_t lo, uint64_t hi,
+                                                    uint64_t run)
+{
+    uint64_t i = lo;
+    for (; i + 8 <= hi; i += 8) {
+        T v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = in[i + q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            out[i + q] = run;
+            run += v[q];
+        }
+    }
+    for (; i < hi; i++) {
+        out[i] = run;
+        run += in[i];
+    }
+    return run;
+}
+
 }  // namespace hufb200

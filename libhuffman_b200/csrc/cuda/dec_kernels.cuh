@@ -267,8 +267,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chunks(DecArgs a)
     const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
     const uint64_t lo = min(n, per * threadIdx.x);
     const uint64_t hi = min(n, lo + per);
-    uint64_t sum = 0;
-    for (uint64_t i = lo; i < hi; i++) sum += a.chunk_cnt[i];
+    const uint64_t sum = range_sum(a.chunk_cnt, lo, hi);
     const uint64_t incl = warp_incl_scan(sum);
     if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
     __syncthreads();
@@ -278,11 +277,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chunks(DecArgs a)
         warp_tot[lane_id()] = ti - t;
     }
     __syncthreads();
-    uint64_t run = warp_tot[warp_in_cta()] + incl - sum;
-    for (uint64_t i = lo; i < hi; i++) {
-        a.chunk_off[i] = run;
-        run += a.chunk_cnt[i];
-    }
+    const uint64_t run = range_excl_scan(a.chunk_cnt, a.chunk_off, lo, hi, warp_tot[warp_in_cta()] + incl - sum);
     if (hi == n && lo < n) {
         a.chunk_off[n] = run;
         a.result[0] = run < a.max_cand ? run : a.max_cand;
@@ -320,8 +315,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_olen(DecArgs a)
     const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
     const uint64_t lo = min(n, per * threadIdx.x);
     const uint64_t hi = min(n, lo + per);
-    uint64_t sum = 0;
-    for (uint64_t i = lo; i < hi; i++) sum += a.olen[i];
+    const uint64_t sum = range_sum(a.olen, lo, hi);
     const uint64_t incl = warp_incl_scan(sum);
     if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
     __syncthreads();
@@ -331,11 +325,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_olen(DecArgs a)
         warp_tot[lane_id()] = ti - t;
     }
     __syncthreads();
-    uint64_t run = a.out_base + warp_tot[warp_in_cta()] + incl - sum;
-    for (uint64_t i = lo; i < hi; i++) {
-        a.out_off[i] = run;
-        run += a.olen[i];
-    }
+    const uint64_t run = range_excl_scan(a.olen, a.out_off, lo, hi, a.out_base + warp_tot[warp_in_cta()] + incl - sum);
     if (hi == n && lo < n) a.out_off[n] = run;
     if (n == 0 && threadIdx.x == 0) a.out_off[0] = a.out_base;
 }

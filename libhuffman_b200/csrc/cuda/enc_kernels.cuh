@@ -433,8 +433,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_sizes(const uint64_t *__r
     const uint64_t lo = min(n, per * threadIdx.x);
     const uint64_t hi = min(n, lo + per);
 
-    uint64_t sum = 0;
-    for (uint64_t i = lo; i < hi; i++) sum += in[i];
+    const uint64_t sum = range_sum(in, lo, hi);
 
     const uint64_t incl = warp_incl_scan(sum);
     if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
@@ -448,11 +447,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_sizes(const uint64_t *__r
     // out[0] holds the running total of the previous passes (0 for the first pass)
     const uint64_t base = out[0];
     __syncthreads();
-    uint64_t run = base + warp_tot[warp_in_cta()] + incl - sum;
-    for (uint64_t i = lo; i < hi; i++) {
-        out[i] = run;
-        run += in[i];
-    }
+    const uint64_t run = range_excl_scan(in, out, lo, hi, base + warp_tot[warp_in_cta()] + incl - sum);
     if (hi == n && lo < n) {
         out[n] = run;
         if (run > cap) atomicMax(&status[0], (uint32_t)kErrNoMem);
