@@ -38,6 +38,9 @@ def small_cases():
         ("segment_edge_32769", datagen.zipf(32769 + 16, 200, seed=9), 32769),
         ("short_last_block", datagen.zipf(3 * 4096 + 5, 100, seed=10), 4096),
         ("random_many_ties", (rng.integers(0, 200, 9000) // 7).astype(np.uint8).tobytes(), 2048),
+        # half the block is a run of one symbol (2-bit code), half is spread over 255 symbols: the
+        # average code length oversizes the decoder's optimistic sub-blocks inside the run
+        ("run_then_uniform_64k", bytes([7]) * 32768 + datagen.uniform(32768, 255, seed=6), 65536),
     ]
     return c
 
