@@ -74,6 +74,77 @@ __device__ __forceinline__ void prefetch_l2(const void *p)
 #endif
 }
 
+// Shared memory through explicit shared-window addresses (32-bit registers on the device):
+// the hot decode loop keeps its table and stage bases in plain registers, so the compiler has
+// no generic pointer whose window base it would rebuild (S2R + LEA) inside the loop, and an
+// aligned table base can be OR-ed into the index (one LOP3 instead of clamp + add).
+#ifdef HUF_EMU
+typedef uintptr_t saddr_t;
+inline saddr_t smem_addr(const void *p) { return reinterpret_cast<uintptr_t>(p); }
+inline saddr_t saddr_or(saddr_t base, uint32_t off) { return base + off; }
+inline saddr_t saddr_pin(saddr_t a) { return a; }
+inline uint32_t lds_u16(saddr_t a) { return *reinterpret_cast<const uint16_t *>(a); }
+inline uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t *>(a); }
+inline void lds_u32x2(saddr_t a, uint32_t &w0, uint32_t &w1)
+{
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(a);
+    w0 = p[0];
+    w1 = p[1];
+}
+inline void lds_u32x3(saddr_t a, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+{
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(a);
+    w0 = p[0];
+    w1 = p[1];
+    w2 = p[2];
+}
+inline void sts_u32(saddr_t a, uint32_t v) { *reinterpret_cast<uint32_t *>(a) = v; }
+inline void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t *>(a) = (uint8_t)v; }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ saddr_t smem_addr(const void *p) { return (saddr_t)__cvta_generic_to_shared(p); }
+// Pins an address in a register: the value becomes opaque to the compiler, which would
+// otherwise rebuild it from the window base next to every use.
+__device__ __forceinline__ saddr_t saddr_pin(saddr_t a)
+{
+    saddr_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+// base must be aligned beyond every bit of off
+__device__ __forceinline__ saddr_t saddr_or(saddr_t base, uint32_t off) { return base | off; }
+__device__ __forceinline__ uint32_t lds_u16(saddr_t a)
+{
+    uint32_t v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(saddr_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_u32x2(saddr_t a, uint32_t &w0, uint32_t &w1)
+{
+    asm volatile("ld.shared.u32 %0, [%2]; ld.shared.u32 %1, [%2+4];" : "=r"(w0), "=r"(w1) : "r"(a));
+}
+__device__ __forceinline__ void lds_u32x3(saddr_t a, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+{
+    asm volatile("ld.shared.u32 %0, [%3]; ld.shared.u32 %1, [%3+4]; ld.shared.u32 %2, [%3+8];"
+                 : "=r"(w0), "=r"(w1), "=r"(w2)
+                 : "r"(a));
+}
+__device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u8(saddr_t a, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+#endif
+
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
 template <typename T>

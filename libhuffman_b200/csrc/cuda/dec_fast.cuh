@@ -57,13 +57,27 @@ constexpr uint32_t kFastFlags = 0xc0u;
 constexpr uint32_t kMetaFast = 1u;
 
 constexpr int kFT = 128;                  // threads per CTA
-constexpr int kRegStride = 236;           // bytes per thread region (59 words: conflict-free)
-constexpr int kRegPad = 12;               // room in front of the speculative symbols
-constexpr int kRegCap = 224;              // symbols a region can hold behind the pad
+constexpr int kRegWords = 56;             // words per thread region
+constexpr int kRegCap = 4 * kRegWords;    // symbols a region can hold
+constexpr int kRegRow = kFT * 4;          // regions are interleaved: word c of thread t sits at
+                                          // row c, column t -- the bank is the thread's, so region
+                                          // stores and loads never conflict whatever c each lane is at
 constexpr int kMaxSubWords = 27;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
-constexpr int kFastDyn = kFastStage + kFT * kRegStride + 16;
+// Dynamic shared memory of k_decode (the kernel has no static shared memory, so the block
+// starts at shared-window address 0x400 behind the 1 KB the system reserves):
+//   [0, kFastStage)            staged payload / compaction window
+//   [kFastStage, kFastLutOff)  FastSmall: per-thread hand-over words and CTA scalars
+//   [kFastLutOff, +8 KB)       lookup table, at window address 0x4000: 8 KB aligned, so the
+//                              table index is OR-ed into the base
+//   [kFastRegOff, ...)         symbol regions, one per thread
+//   [kFastTailOff, kFastDyn)   FastTail: long-code records, re-speculation classes
+// kFastDyn + 1 KB is exactly a quarter of the 228 KB an SM offers: four CTAs per SM.
+constexpr int kFastLutOff = 15360;
+constexpr int kFastLutAlign = 2 * kLutSize;               // 8 KB
+constexpr int kFastRegOff = kFastLutOff + 2 * kLutSize;
+constexpr int kFastTailOff = kFastRegOff + kRegWords * kRegRow;
 
 constexpr int kRespecMin = 2;             // threads still failing after one repair round: a ripple, re-speculate
 constexpr int kRespecStarts = 16;         // warm-up start offsets tried for the alternate trajectory
@@ -251,94 +265,123 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
 // K5: fast block decode.
 // ------------------------------------------------------------------------------------------
 
-struct FastSmem {
-    __align__(16) uint16_t lut[kLutSize + 8];  // [kLutSize] = sentinel: root bit set
+struct FastSmall {
     uint32_t sub_end[kFT];
-    uint32_t long_code[kLongMax];  // left-aligned code words longer than the table reach, ascending
-    uint16_t long_ent[kLongMax];   // length << 8 | symbol
-    uint32_t nlong;
-    unsigned long long next_j;
-    uint32_t c_start[2][kFT];      // re-speculation: first code word of the primary / alternate
-    uint32_t c_end[2][kFT];        // trajectory of every sub-block and where it leaves it
     uint32_t pred[kFT];            // predicted true start of every sub-block
     uint32_t warp_tot[kFT / 32];
+    uint32_t nlong;
     uint32_t redo;
     uint32_t fin_found;
     uint32_t fin_end;
     uint32_t total;
+    unsigned long long next_j;
 };
 
-// Table entry for the code word that starts at staged bit `pos` (stateless: two words + shift).
-__device__ __forceinline__ uint32_t fast_look(const uint32_t *sw, const uint16_t *lut, uint32_t pos)
+struct FastTail {
+    uint32_t long_code[kLongMax];  // left-aligned code words longer than the table reach, ascending
+    uint32_t c_start[2][kFT];      // re-speculation: first code word of the primary / alternate
+    uint32_t c_end[2][kFT];        // trajectory of every sub-block and where it leaves it
+    uint16_t long_ent[kLongMax];   // length << 8 | symbol
+};
+
+constexpr int kFastDyn = kFastTailOff + (int)sizeof(FastTail);
+static_assert(kFastStage + (int)sizeof(FastSmall) <= kFastLutOff, "FastSmall must fit in front of the table");
+static_assert(kFastStage % 16 == 0 && kFastRegOff % 16 == 0 && kFastTailOff % 8 == 0, "alignment");
+
+// Byte offset of the table entry selected by the twelve bits BEHIND the root bit of the left
+// aligned window (every code word starts with the 0 bit of the one-child root, src/tree.c:410-413).
+// The root bit itself is checked separately: a walk on a set root bit is dead.
+__device__ __forceinline__ uint32_t fast_idx(uint32_t win) { return (win >> (32 - kTreeReach - 1)) & (2u * kLutSize - 2u); }
+
+// The three staged words from the one that holds bit `pos` on, kept in registers while a walk
+// moves through its sub-block: every staged word is loaded once per walk (the loads of 32
+// lanes at unrelated positions hit random banks, so each one costs several wavefronts).
+struct BitWin {
+    uint32_t w0, w1, w2;
+};
+
+__device__ __forceinline__ void win_load(BitWin &b, saddr_t sw_s, uint32_t pos)
 {
-    const uint32_t wi = pos >> 5;
-    const uint32_t win = __funnelshift_l(sw[wi + 1], sw[wi], pos);
-    return lut[min(win >> (32 - kTreeReach), (uint32_t)kLutSize)];
+    lds_u32x3(sw_s + ((pos >> 5) << 2), b.w0, b.w1, b.w2);
 }
 
-// Four consecutive table entries from `pos` on: three staged words are loaded once into a
-// 64-bit left-aligned bit buffer that is shifted by every code length (4 x 13 bits fit).
-// Positions advance by bits [3:0] of each entry.  Returns the position behind the fourth.
-__device__ __forceinline__ uint32_t fast_look4(const uint32_t *sw, const uint16_t *lut, uint32_t pos,
-                                               uint32_t &e0, uint32_t &e1, uint32_t &e2, uint32_t &e3,
-                                               uint32_t &last_start)
+// The walk moved from `pos` to `np` (at most two words further).
+__device__ __forceinline__ void win_advance(BitWin &b, saddr_t sw_s, uint32_t pos, uint32_t np)
 {
-    const uint32_t wi = pos >> 5;
-    const uint32_t w0 = sw[wi], w1 = sw[wi + 1], w2 = sw[wi + 2];
-    uint32_t hi = __funnelshift_l(w1, w0, pos);  // stream bits pos .. pos+31
-    uint32_t lo = __funnelshift_l(w2, w1, pos);  // stream bits pos+32 .. pos+63
-    e0 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l0 = e0 & 0xfu;
-    hi = __funnelshift_l(lo, hi, l0);
-    lo <<= l0;
-    e1 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l1 = e1 & 0xfu;
-    hi = __funnelshift_l(lo, hi, l1);
-    lo <<= l1;
-    e2 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l2 = e2 & 0xfu;
-    hi = __funnelshift_l(lo, hi, l2);
-    e3 = lut[min(hi >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    const uint32_t l3 = e3 & 0xfu;
-    last_start = pos + l0 + l1 + l2;  // where the fourth code word starts
-    return last_start + l3;
-}
-
-// One exact decode step at staged bit position `pos`: true + symbol when a code word starts
-// there (table hit or long-code record), false when the walk dies (pos advances one bit: any
-// deterministic rule serves a speculative start, and a dead step on the proven trajectory sends
-// the block to the general lane).
-__device__ __noinline__ bool fast_step(const uint32_t *sw, const FastSmem &sm, uint32_t &pos,
-                                       uint32_t &sym)
-{
-    const uint32_t wi = pos >> 5;
-    const uint32_t win = __funnelshift_l(sw[wi + 1], sw[wi], pos);
-    const uint32_t e = sm.lut[min(win >> (32 - kTreeReach), (uint32_t)kLutSize)];
-    if (!(e & kFastFlags)) {
-        sym = e >> 8;
-        pos += e & 0xffu;
-        return true;
+    const uint32_t adv = (np >> 5) - (pos >> 5);
+    if (adv) {
+        const saddr_t at = sw_s + ((np >> 5) << 2);
+        const uint32_t n2 = lds_u32(at + 8);
+        if (adv == 1) {
+            b.w0 = b.w1;
+            b.w1 = b.w2;
+        } else {
+            b.w0 = b.w2;
+            b.w1 = lds_u32(at + 4);
+        }
+        b.w2 = n2;
     }
-    if ((e & 0x80u) && sm.nlong) {
+}
+
+// Four consecutive table entries from `pos` on: the three window words are shifted into a
+// 64-bit left-aligned bit buffer that is then shifted by every code length (4 x 13 bits fit; the
+// shifter takes the low five bits of an entry, i.e. its length, 1 for the special kinds).
+// Returns the position behind the fourth.  h0..h3 are the four windows: their top bits tell
+// whether a walk started on a set root bit; the entries and the returned position are only
+// meaningful up to the first such walk (it is dead and advances one bit).
+__device__ __forceinline__ uint32_t fast_look4(const BitWin &b, saddr_t lut_s, uint32_t pos,
+                                               uint32_t &e0, uint32_t &e1, uint32_t &e2, uint32_t &e3,
+                                               uint32_t &h0, uint32_t &h1, uint32_t &h2, uint32_t &h3)
+{
+    const uint32_t w0 = b.w0, w1 = b.w1, w2 = b.w2;
+    h0 = __funnelshift_l(w1, w0, pos);                 // stream bits pos .. pos+31
+    uint32_t lo = __funnelshift_l(w2, w1, pos);        // stream bits pos+32 .. pos+63
+    e0 = lds_u16(saddr_or(lut_s, fast_idx(h0)));
+    h1 = __funnelshift_l(lo, h0, e0);
+    lo = __funnelshift_l(0u, lo, e0);
+    e1 = lds_u16(saddr_or(lut_s, fast_idx(h1)));
+    h2 = __funnelshift_l(lo, h1, e1);
+    lo = __funnelshift_l(0u, lo, e1);
+    e2 = lds_u16(saddr_or(lut_s, fast_idx(h2)));
+    h3 = __funnelshift_l(lo, h2, e2);
+    e3 = lds_u16(saddr_or(lut_s, fast_idx(h3)));
+    // lengths sit in bits [3:0], bits [5:4] are clear in every kind of entry: no carries
+    return pos + ((e0 + e1 + e2 + e3) & 0x3fu);
+}
+
+// One exact decode step at staged bit position `pos`.  Returns the next position in the low
+// word; bit 63 is set, with the symbol in bits [39:32], when a code word starts at `pos` (table
+// hit or long-code record).  A dead walk (set root bit, absent child) advances one bit: any
+// deterministic rule serves a speculative start -- this one re-synchronises quickly on skewed
+// codes -- and a dead step on the proven trajectory sends the block to the general lane.
+constexpr uint64_t kStepOk = 1ull << 63;
+__device__ __noinline__ uint64_t fast_step(saddr_t sw_s, saddr_t lut_s, const FastTail *ft, uint32_t n,
+                                           uint32_t pos)
+{
+    uint32_t w0, w1;
+    lds_u32x2(sw_s + ((pos >> 5) << 2), w0, w1);
+    const uint32_t win = __funnelshift_l(w1, w0, pos);
+    const uint32_t e = lds_u16(saddr_or(lut_s, fast_idx(win)));
+    const uint32_t root = win >> 31;
+    if (!((e & kFastFlags) | root)) {
+        return kStepOk | ((uint64_t)(e >> 8) << 32) | (pos + (e & 0xfu));
+    }
+    if (!root && (e & 0x80u) && n) {
         // last record with code <= window (prefix-free codes: the only possible match), found
         // with a fixed number of halving steps
-        const uint32_t n = sm.nlong;
         uint32_t lo = 0;
 #pragma unroll
         for (uint32_t step = kLongMax / 2; step; step >>= 1) {
             const uint32_t mid = lo + step;
-            if (mid < n && sm.long_code[mid] <= win) lo = mid;
+            if (mid < n && ft->long_code[mid] <= win) lo = mid;
         }
-        const uint32_t ent = sm.long_ent[lo];
+        const uint32_t ent = ft->long_ent[lo];
         const uint32_t len = ent >> 8;
-        if (((win ^ sm.long_code[lo]) >> (32 - len)) == 0) {
-            sym = ent & 0xffu;
-            pos += len;
-            return true;
+        if (((win ^ ft->long_code[lo]) >> (32 - len)) == 0) {
+            return kStepOk | ((uint64_t)(ent & 0xffu) << 32) | (pos + len);
         }
     }
-    pos += 1;
-    return false;
+    return pos + 1;
 }
 
 // CTA barrier behind divergent per-thread loops: the warp is explicitly reconverged first
@@ -353,25 +396,26 @@ __device__ __forceinline__ void cta_sync()
     __syncthreads();
 }
 
-// Copy n bytes between two shared-memory locations of arbitrary alignment: up to three bytes to
-// align the destination, then whole words assembled with one funnel shift each (four per
-// iteration), then up to three bytes.
-__device__ __forceinline__ void smem_copy(uint8_t *dst, const uint8_t *src, uint32_t n)
+// Copy symbols [s0, s0 + n) of an interleaved region (word j of the region at regw[j * kFT])
+// to dst (shared memory, arbitrary alignment): up to three bytes to align the destination, then
+// whole words assembled with one funnel shift each, then up to three bytes.
+__device__ __forceinline__ void region_copy(uint8_t *dst, const uint32_t *regw, uint32_t s0, uint32_t n)
 {
+    auto sym = [&](uint32_t i) -> uint8_t { return (uint8_t)(regw[(i >> 2) * kFT] >> (8 * (i & 3))); };
     const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
-    if (head > 0) dst[0] = src[0];
-    if (head > 1) dst[1] = src[1];
-    if (head > 2) dst[2] = src[2];
-    // source bytes head.. : word k = funnel(s[k], s[k + 1], sh)
-    const uintptr_t sp = reinterpret_cast<uintptr_t>(src + head);
-    const uint32_t sh = (uint32_t)(sp & 3) * 8;
-    const uint32_t *s = reinterpret_cast<const uint32_t *>(sp & ~uintptr_t(3));
-    uint32_t *d = reinterpret_cast<uint32_t *>(dst + head);
+    if (head > 0) dst[0] = sym(s0);
+    if (head > 1) dst[1] = sym(s0 + 1);
+    if (head > 2) dst[2] = sym(s0 + 2);
+    const uint32_t sb = s0 + head;
+    const uint32_t sh = (sb & 3) * 8;
+    const uint32_t *__restrict__ sp = regw + (sb >> 2) * kFT;
+    uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(dst + head);
     const uint32_t nw = (n - head) >> 2;
-    uint32_t prev = s[0];
+    uint32_t prev = sp[0];
     uint32_t k = 0;
     for (; k + 4 <= nw; k += 4) {
-        const uint32_t a1 = s[k + 1], a2 = s[k + 2], a3 = s[k + 3], a4 = s[k + 4];
+        const uint32_t a1 = sp[(k + 1) * kFT], a2 = sp[(k + 2) * kFT], a3 = sp[(k + 3) * kFT],
+                       a4 = sp[(k + 4) * kFT];
         d[k] = __funnelshift_r(prev, a1, sh);
         d[k + 1] = __funnelshift_r(a1, a2, sh);
         d[k + 2] = __funnelshift_r(a2, a3, sh);
@@ -379,15 +423,32 @@ __device__ __forceinline__ void smem_copy(uint8_t *dst, const uint8_t *src, uint
         prev = a4;
     }
     for (; k < nw; k++) {
-        const uint32_t a1 = s[k + 1];
+        const uint32_t a1 = sp[(k + 1) * kFT];
         d[k] = __funnelshift_r(prev, a1, sh);
         prev = a1;
     }
     const uint32_t done = head + 4 * nw;
-    if (done < n) dst[done] = src[done];
-    if (done + 1 < n) dst[done + 1] = src[done + 1];
-    if (done + 2 < n) dst[done + 2] = src[done + 2];
+    if (done < n) dst[done] = sym(s0 + done);
+    if (done + 1 < n) dst[done + 1] = sym(s0 + done + 1);
+    if (done + 2 < n) dst[done + 2] = sym(s0 + done + 2);
 }
+
+// Phase timing of thread 0 of every CTA (debug builds with -DHUF_PHASE_PROF only): cycles per
+// phase are summed over all CTAs into g_fast_prof, scripts/phase_prof.py prints them.
+#ifdef HUF_PHASE_PROF
+__device__ unsigned long long g_fast_prof[16];
+#define HUF_PROF(k)                                \
+    if (tid == 0) {                                \
+        const unsigned long long now_ = clock64(); \
+        pacc[k] += now_ - pt;                      \
+        pt = now_;                                 \
+    }
+#define HUF_PROF_CNT(k) \
+    if (tid == 0) pacc[k]++;
+#else
+#define HUF_PROF(k)
+#define HUF_PROF_CNT(k)
+#endif
 
 __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
 {
@@ -396,12 +457,23 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
 #else
     extern __shared__ __align__(16) uint8_t dyn[];
 #endif
-    __shared__ FastSmem sm;
+    FastSmall &sm = *reinterpret_cast<FastSmall *>(dyn + kFastStage);
+    FastTail &ft = *reinterpret_cast<FastTail *>(dyn + kFastTailOff);
     const int tid = threadIdx.x;
+#ifdef HUF_PHASE_PROF
+    unsigned long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long pt = clock64();
+#endif
     const uint64_t ncand = a.result[0];
     uint32_t *sw = reinterpret_cast<uint32_t *>(dyn);  // staged payload, big-endian words
-    uint8_t *regions = dyn + kFastStage;
-    uint8_t *reg = regions + tid * kRegStride;
+    uint16_t *lut = reinterpret_cast<uint16_t *>(dyn + kFastLutOff);
+    uint8_t *regions = dyn + kFastRegOff;
+    const uint32_t *regw = reinterpret_cast<const uint32_t *>(regions) + tid;  // my region: regw[c * kFT]
+    const saddr_t sw_s = saddr_pin(smem_addr(sw)), lut_s = saddr_pin(smem_addr(lut));
+    const saddr_t reg_s = saddr_pin(smem_addr(regw));  // first word of my region
+#ifndef HUF_EMU
+    if (lut_s & (uint32_t)(kFastLutAlign - 1)) __trap();  // the table base is OR-ed into its index
+#endif
     const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
     for (;;) {
@@ -445,11 +517,10 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             const uint32_t *src = a.terms + j * kTermStride;
             for (uint32_t k = tid; k < nterm; k += kFT) tb[k] = src[k];
             for (uint32_t r = tid; r < nlong; r += kFT) {
-                sm.long_code[r] = src[kTermStride - 2 * (r + 1)];
-                sm.long_ent[r] = (uint16_t)src[kTermStride - 2 * (r + 1) + 1];
+                ft.long_code[r] = src[kTermStride - 2 * (r + 1)];
+                ft.long_ent[r] = (uint16_t)src[kTermStride - 2 * (r + 1) + 1];
             }
             if (tid == 0) {
-                sm.lut[kLutSize] = (uint16_t)kFastDead;
                 sm.redo = 0;
                 sm.nlong = nlong;
             }
@@ -476,12 +547,14 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             }
 #pragma unroll
             for (int q = 0; q < kPer / 8; q++) {
-                reinterpret_cast<uint4 *>(sm.lut)[tid * (kPer / 8) + q] =
+                reinterpret_cast<uint4 *>(lut)[tid * (kPer / 8) + q] =
                     make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             }
         }
         cta_sync();
 
+        HUF_PROF(0);
+        HUF_PROF_CNT(9);
         // ---- chunk loop
         const uint64_t next_cand = (j + 1 < ncand) ? a.cand[j + 1] : a.avail;
         const uint64_t room_end = 8ull * a.avail;
@@ -493,7 +566,8 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
         const uint64_t out0 = a.out_off[j];
         const bool can_write = !a.count_only && out0 + orig_len <= a.out_cap;
         uint32_t sub_cap_w = min((uint32_t)kMaxSubWords, (kRegCap * min_len) / 32u);
-        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 7, so never below 7
+        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 7, so never below 7 (odd: the staged
+                                            // words of the threads of a warp start in different banks)
         // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
         uint32_t warm = 160;
         if (use_guess) {
@@ -501,8 +575,36 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             warm = (uint32_t)(w < 64 ? 64 : (w > 320 ? 320 : w));
         }
         uint32_t status = kOk;
+        // staged 16-byte pieces of a thread (piece tid + q * kFT of the chunk), loaded with all
+        // requests in flight together; the next chunk's are requested before the current chunk
+        // is copied out, so their latency hides behind the copy-out
+        constexpr int kStageIter = (kFastStage / 16 + kFT - 1) / kFT;
+        uint4 v[kStageIter];
+        bool pre_ok = false;
+        uint64_t pre_base = 0;
+        uint32_t pre_n16 = 0, cur_n16 = 0;
+        auto stage_issue = [&](uint64_t from16, uint32_t n16) {
+#pragma unroll
+            for (int q = 0; q < kStageIter; q++) {
+                const uint32_t c = (uint32_t)tid + (uint32_t)q * kFT;
+                const uint64_t byte = from16 + 16ull * c;
+                v[q] = make_uint4(0, 0, 0, 0);
+                if (c < n16) {
+                    if (byte + 16 <= a.avail) {
+                        v[q] = ld_stream_u4(a.in + byte);
+                    } else if (byte < a.avail) {
+                        uint32_t w[4] = {0, 0, 0, 0};
+                        for (int r = 0; r < 16; r++) {
+                            if (byte + r < a.avail) w[r >> 2] |= (uint32_t)a.in[byte + r] << (8 * (r & 3));
+                        }
+                        v[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        };
 
         for (;;) {
+            HUF_PROF_CNT(7);
             const uint64_t limit = use_guess ? guess_end : room_end;
             if (next_bit >= limit) {
                 if (use_guess) {
@@ -539,46 +641,64 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 const uint64_t nxt = base16 + ((cover + 7) >> 3) + 128ull * (uint32_t)tid;
                 if (nxt < a.avail && 128u * (uint32_t)tid < (kFT * sub >> 3) + 256u) prefetch_l2(a.in + nxt);
                 const uint32_t n16 = ((cover + 7) >> 3) / 16 + 2;
-                for (uint32_t c = tid; c < n16; c += kFT) {
-                    const uint64_t byte = base16 + 16ull * c;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (byte + 16 <= a.avail) {
-                        v = ld_stream_u4(a.in + byte);
-                    } else if (byte < a.avail) {
-                        uint32_t w[4] = {0, 0, 0, 0};
-                        for (int q = 0; q < 16; q++) {
-                            if (byte + q < a.avail) w[q >> 2] |= (uint32_t)a.in[byte + q] << (8 * (q & 3));
-                        }
-                        v = make_uint4(w[0], w[1], w[2], w[3]);
+                // the loads were issued in front of the previous chunk's copy-out when it
+                // predicted this chunk (same base, at least as long); otherwise they are now
+                if (!(pre_ok && pre_base == base16 && pre_n16 >= n16)) stage_issue(base16, n16);
+                pre_ok = false;
+                cur_n16 = n16;
+#pragma unroll
+                for (int q = 0; q < kStageIter; q++) {
+                    const uint32_t c = (uint32_t)tid + (uint32_t)q * kFT;
+                    if (c < n16) {
+                        reinterpret_cast<uint4 *>(sw)[c] =
+                            make_uint4(bswap32(v[q].x), bswap32(v[q].y), bswap32(v[q].z), bswap32(v[q].w));
                     }
-                    reinterpret_cast<uint4 *>(sw)[c] =
-                        make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
                 }
             }
             cta_sync();
+            HUF_PROF(1);
 
             // (1) warm-up in front of my sub-block, then decode it into my region
             const uint32_t my_lo = tid == 0 ? rel_start : min(A + (uint32_t)tid * sub, cover);
             const uint32_t my_hi = min(A + (uint32_t)(tid + 1) * sub, cover);
             uint32_t pos = my_lo, cnt = 0, last_dead = kNone;
-            // blind walk (every entry advances by its length field, specials by one bit) from
-            // `from` to the first position >= limit
+            // blind walk (every entry advances by its length field, specials and walks on a
+            // set root bit by one bit) from `from` to the first position >= limit
             auto blind_to = [&](uint32_t from, uint32_t limit) -> uint32_t {
                 uint32_t p = from;
-                // four steps at a time while all four start in front of the limit
-                while (p < limit) {
-                    uint32_t e0, e1, e2, e3, p3;
-                    const uint32_t np = fast_look4(sw, sm.lut, p, e0, e1, e2, e3, p3);
-                    if (p3 >= limit) {
-                        // the fourth starts behind the limit: take the steps in front of it
-                        if (p < limit) p += e0 & 0xfu;
-                        if (p < limit) p += e1 & 0xfu;
-                        if (p < limit) p += e2 & 0xfu;
-                        break;
+                if (p >= limit) return p;
+                BitWin b;
+                win_load(b, sw_s, p);
+                for (;;) {
+                    // like fast_look4, with the length of a walk on a set root bit forced to 1
+                    // (mask = all ones under a set root bit, computed beside the table load)
+                    const uint32_t h0 = __funnelshift_l(b.w1, b.w0, p);
+                    uint32_t lo = __funnelshift_l(b.w2, b.w1, p);
+                    uint32_t m = (uint32_t)((int32_t)h0 >> 31);
+                    const uint32_t l0 = (lds_u16(saddr_or(lut_s, fast_idx(h0))) & ~m) | (m & 1u);
+                    const uint32_t h1 = __funnelshift_l(lo, h0, l0);
+                    lo = __funnelshift_l(0u, lo, l0);
+                    m = (uint32_t)((int32_t)h1 >> 31);
+                    const uint32_t l1 = (lds_u16(saddr_or(lut_s, fast_idx(h1))) & ~m) | (m & 1u);
+                    const uint32_t h2 = __funnelshift_l(lo, h1, l1);
+                    lo = __funnelshift_l(0u, lo, l1);
+                    m = (uint32_t)((int32_t)h2 >> 31);
+                    const uint32_t l2 = (lds_u16(saddr_or(lut_s, fast_idx(h2))) & ~m) | (m & 1u);
+                    const uint32_t h3 = __funnelshift_l(lo, h2, l2);
+                    m = (uint32_t)((int32_t)h3 >> 31);
+                    const uint32_t l3 = (lds_u16(saddr_or(lut_s, fast_idx(h3))) & ~m) | (m & 1u);
+                    const uint32_t np = p + ((l0 + l1 + l2 + l3) & 0x3fu);
+                    if (np < limit) {  // four steps at a time while the fifth starts in front of the limit
+                        win_advance(b, sw_s, p, np);
+                        p = np;
+                        continue;
                     }
-                    p = np;
+                    p += l0 & 0x1fu;
+                    if (p < limit) p += l1 & 0x1fu;
+                    if (p < limit) p += l2 & 0x1fu;
+                    if (p < limit) p += l3 & 0x1fu;
+                    return p;
                 }
-                return p;
             };
             // start `warm` bits early (or at the proven chunk start when that is closer)
             const uint32_t warm_from = my_lo > rel_start + warm ? my_lo - warm : rel_start;
@@ -594,57 +714,79 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             for (int round = 0; round <= kFT; round++) {
                 if (walk) {
                     pos = start;
-                    cnt = 0;
                     last_dead = kNone;
+                    // Symbol number n of my region lives in byte n & 3 of word n >> 2.  Only whole
+                    // words are stored: up to three pending symbols wait in the top bytes of
+                    // `acc` (earliest lowest), so a group of four always leaves as one 32-bit
+                    // store even after single steps have left the count unaligned.
+                    saddr_t wp = reg_s;            // word the next store goes to
+                    uint32_t acc = 0, npend = 0;   // pending symbols
+                    uint32_t sh = 32;              // 32 - 8 * npend
+                    auto put = [&](uint32_t sy) {
+                        acc = (acc >> 8) | (sy << 24);
+                        npend++;
+                        if (npend == 4) {
+                            sts_u32(wp, acc);
+                            wp += kRegRow;
+                            npend = 0;
+                        }
+                        sh = 32 - 8 * npend;
+                    };
+                    BitWin b;
+                    if (pos < my_hi) win_load(b, sw_s, pos);
                     while (pos < my_hi) {
-                        uint32_t e0, e1, e2, e3, p3;
-                        const uint32_t np = fast_look4(sw, sm.lut, pos, e0, e1, e2, e3, p3);
-                        if (!((e0 | e1 | e2 | e3) & kFastFlags)) {
+                        uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
+                        const uint32_t np = fast_look4(b, lut_s, pos, e0, e1, e2, e3, h0, h1, h2, h3);
+                        if (!(((e0 | e1 | e2 | e3) & kFastFlags) | ((h0 | h1 | h2 | h3) >> 31))) {
                             // four plain table hits
-                            if (p3 < my_hi) {
-                                // ... that all start inside my sub-block: one 32-bit store (four
-                                // byte stores while a long code word has left the count unaligned)
+                            const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
+                            const uint32_t hi2 = __byte_perm(e2, e3, 0x0051);
+                            const uint32_t four = __byte_perm(lo2, hi2, 0x5410);
+                            if (np <= my_hi) {
+                                // ... that all start inside my sub-block: one 32-bit store
+                                win_advance(b, sw_s, pos, np);
                                 pos = np;
-                                const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
-                                const uint32_t hi2 = __byte_perm(e2, e3, 0x0051);
-                                const uint32_t four = __byte_perm(lo2, hi2, 0x5410);
-                                if (!(cnt & 3)) {
-                                    *reinterpret_cast<uint32_t *>(reg + kRegPad + cnt) = four;
-                                } else {
-                                    reg[kRegPad + cnt] = (uint8_t)four;
-                                    reg[kRegPad + cnt + 1] = (uint8_t)(four >> 8);
-                                    reg[kRegPad + cnt + 2] = (uint8_t)(four >> 16);
-                                    reg[kRegPad + cnt + 3] = (uint8_t)(four >> 24);
-                                }
-                                cnt += 4;
+                                sts_u32(wp, __funnelshift_rc(acc, four, sh));  // pending bytes below, new ones above
+                                acc = four;                                    // its top bytes are the new pending ones
+                                wp += kRegRow;
                                 continue;
                             }
-                            // the fourth starts behind the boundary: at most three are mine
-                            reg[kRegPad + cnt++] = (uint8_t)(e0 >> 8);
+                            // the sub-block ends among them: the first is mine, the others may be
+                            put(four & 0xffu);
                             pos += e0 & 0xfu;
                             if (pos < my_hi) {
-                                reg[kRegPad + cnt++] = (uint8_t)(e1 >> 8);
+                                put((four >> 8) & 0xffu);
                                 pos += e1 & 0xfu;
                             }
                             if (pos < my_hi) {
-                                reg[kRegPad + cnt++] = (uint8_t)(e2 >> 8);
+                                put((four >> 16) & 0xffu);
                                 pos += e2 & 0xfu;
+                            }
+                            if (pos < my_hi) {
+                                put(four >> 24);
+                                pos += e3 & 0xfu;
                             }
                             break;
                         }
-                        // irregular (special entry among the four): one exact step
-                        const uint32_t at = pos;
-                        uint32_t sy;
-                        if (fast_step(sw, sm, pos, sy)) {
-                            reg[kRegPad + cnt] = (uint8_t)sy;
-                            cnt++;
-                        } else {
-                            last_dead = at;
+                        // irregular (special entry or dead root among the four): one exact step
+                        {
+                            const uint32_t at = pos;
+                            const uint64_t r = fast_step(sw_s, lut_s, &ft, sm.nlong, pos);
+                            pos = (uint32_t)r;
+                            if (r & kStepOk) {
+                                put((uint32_t)(r >> 32) & 0xffu);
+                            } else {
+                                last_dead = at;
+                            }
                         }
+                        if (pos < my_hi) win_load(b, sw_s, pos);
                     }
+                    if (npend) sts_u32(wp, acc >> sh);
+                    cnt = (uint32_t)((wp - reg_s) / (uint32_t)kRegRow) * 4u + npend;
                     end = pos;
                     sm.sub_end[tid] = end;
                 }
+                if (round == 0) HUF_PROF(2);
                 cta_sync();
                 const uint32_t want = (tid == 0 || (uint32_t)tid >= nact) ? start : sm.sub_end[tid - 1];
                 walk = want != start;
@@ -652,6 +794,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 start = want;
                 __syncwarp();
                 const int nfail = __syncthreads_count(walk);
+                if (nfail) HUF_PROF_CNT(8);
                 if (nfail == 0) break;
                 if (round == 1 && nfail >= kRespecMin) {
                     // Re-speculation.  Isolated failures are gone after one repair round; threads
@@ -672,22 +815,22 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                         }
                         if (alt != kNone) alt_end = blind_to(alt, my_hi);
                     }
-                    sm.c_start[0][tid] = had;
-                    sm.c_end[0][tid] = end;
-                    sm.c_start[1][tid] = alt;
-                    sm.c_end[1][tid] = alt_end;
+                    ft.c_start[0][tid] = had;
+                    ft.c_end[0][tid] = end;
+                    ft.c_start[1][tid] = alt;
+                    ft.c_end[1][tid] = alt_end;
                     cta_sync();
                     if (tid == 0) {
-                        uint32_t cur = sm.c_end[0][0];  // thread 0 decoded from the proven start
-                        sm.pred[0] = sm.c_start[0][0];
+                        uint32_t cur = ft.c_end[0][0];  // thread 0 decoded from the proven start
+                        sm.pred[0] = ft.c_start[0][0];
                         for (uint32_t t = 1; t < nact; t++) {
                             sm.pred[t] = cur;
-                            if (cur == sm.c_start[0][t]) {
-                                cur = sm.c_end[0][t];
-                            } else if (cur == sm.c_start[1][t]) {
-                                cur = sm.c_end[1][t];
+                            if (cur == ft.c_start[0][t]) {
+                                cur = ft.c_end[0][t];
+                            } else if (cur == ft.c_start[1][t]) {
+                                cur = ft.c_end[1][t];
                             } else {
-                                cur = sm.c_end[0][t];  // unknown class: guess, verification repairs
+                                cur = ft.c_end[0][t];  // unknown class: guess, verification repairs
                             }
                         }
                     }
@@ -698,8 +841,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     }
                 }
             }
-            const uint32_t roff = kRegPad;
-
+            HUF_PROF(3);
             // (3) symbol-count scan
             const uint32_t incl = warp_incl_scan(cnt);
             if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
@@ -721,22 +863,33 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             if (in_blk && !fin && last_dead != kNone) sm.redo = 1;  // dead walk on the proven chain
             if (fin) {
                 // the block ends inside my sub-block: find the bit behind its last code word
+                // (a dead step ends the search: the block goes to the general lane anyway, and
+                // the symbol count of a dead walk does not bound where this one would stop)
                 uint32_t p = start, dead = 0;
-                for (uint32_t q = 0; q < ncopy;) {
-                    uint32_t sy;
-                    if (fast_step(sw, sm, p, sy)) q++; else dead = 1;
+                for (uint32_t q = 0; q < ncopy && !dead;) {
+                    const uint64_t r = fast_step(sw_s, lut_s, &ft, sm.nlong, p);
+                    p = (uint32_t)r;
+                    if (r & kStepOk) q++; else dead = 1;
                 }
                 if (dead) sm.redo = 1;
                 sm.fin_end = p;
                 sm.fin_found = 1;
             }
             cta_sync();
+            HUF_PROF(4);
             if (sm.redo) {
                 status = kRedo;
                 break;
             }
             const bool fin_found = sm.fin_found != 0;
             const uint32_t total_copy = (uint64_t)total < remaining ? total : (uint32_t)remaining;
+            if (!fin_found) {
+                // the block goes on: request the next chunk's payload (same length as this one's)
+                pre_base = ((8ull * base16 + sm.sub_end[nact - 1]) >> 3) & ~uint64_t(15);
+                pre_n16 = cur_n16;
+                stage_issue(pre_base, pre_n16);
+                pre_ok = true;
+            }
 
             // (4) compaction into the (now free) stage buffer, coalesced copy-out
             if (can_write && total_copy) {
@@ -748,23 +901,30 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                 for (uint32_t wb = 0; wb < yend; wb += kFastOutWin) {
                     const uint32_t we = wb + kFastOutWin;
                     const uint32_t c0 = max(y0, wb), c1 = min(y1, we);
-                    if (c0 < c1) smem_copy(obuf + (c0 - wb), reg + roff + (c0 - y0), c1 - c0);
+                    if (c0 < c1) region_copy(obuf + (c0 - wb), regw, c0 - y0, c1 - c0);
                     cta_sync();
+                    HUF_PROF(5);
                     const uint32_t vend = min(yend, we) - wb;          // valid bytes end (window relative)
                     const uint32_t vbeg = wb == 0 ? m : 0;             // valid bytes begin
                     uint8_t *gbase = dst0 - m + wb;                    // 16-byte aligned
                     const uint32_t nlines = (vend + 15) >> 4;
-                    for (uint32_t L = tid; L < nlines; L += kFT) {
-                        const uint32_t b0 = L * 16, b1 = b0 + 16;
-                        if (b0 >= vbeg && b1 <= vend) {
-                            *reinterpret_cast<uint4 *>(gbase + b0) = *reinterpret_cast<const uint4 *>(obuf + b0);
-                        } else {
-                            for (uint32_t q = max(b0, vbeg); q < min(b1, vend); q++) gbase[q] = obuf[q];
-                        }
+                    // whole lines: 16-byte stores; the first and the last line may be partial:
+                    // their bytes go one per thread (threads 0..15 and 16..31)
+                    const uint32_t l_lo = (vbeg + 15) >> 4, l_hi = vend >> 4;
+                    for (uint32_t L = l_lo + tid; L < l_hi; L += kFT) {
+                        *reinterpret_cast<uint4 *>(gbase + 16 * L) = *reinterpret_cast<const uint4 *>(obuf + 16 * L);
+                    }
+                    if (tid < 32) {
+                        // line 0 when it starts late, line l_hi when it ends early (they may coincide)
+                        const uint32_t q = (tid < 16 ? 0u : 16u * l_hi) + ((uint32_t)tid & 15u);
+                        const bool first_part = tid < 16 && l_lo > 0;
+                        const bool last_part = tid >= 16 && l_hi < nlines && (l_hi > 0 || l_lo == 0);
+                        if ((first_part || last_part) && q >= vbeg && q < vend) gbase[q] = obuf[q];
                     }
                     cta_sync();
                 }
             }
+            HUF_PROF(6);
             produced += total_copy;
             if (fin_found) {
                 end_bit = 8ull * base16 + sm.fin_end;
@@ -781,6 +941,11 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             if (status == kRedo) atomicAdd(reinterpret_cast<unsigned long long *>(&a.result[10]), 1ull);
         }
     }
+#ifdef HUF_PHASE_PROF
+    if (tid == 0) {
+        for (int k = 0; k < 10; k++) atomicAdd(&g_fast_prof[k], pacc[k]);
+    }
+#endif
 }
 
 }  // namespace hufb200

@@ -808,3 +808,18 @@ huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
 }
 
 }  // extern "C"
+
+#ifdef HUF_PHASE_PROF
+// Debug builds only (scripts/phase_prof.py): per-phase cycle sums of k_decode.
+extern "C" int huf_b200_debug_phase(unsigned long long *out, int reset)
+{
+    using namespace hufb200;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (out && cudaMemcpyFromSymbol(out, g_fast_prof, 16 * sizeof(unsigned long long)) != cudaSuccess) return -2;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(g_fast_prof, z, sizeof z) != cudaSuccess) return -3;
+    }
+    return 0;
+}
+#endif

@@ -330,6 +330,10 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31));
 }
+inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh < 32 ? sh : 32));
+}
 inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     return (uint32_t)(((((uint64_t)hi << 32) | lo) << (sh & 31)) >> 32);
