@@ -64,6 +64,23 @@ __device__ __forceinline__ void cp_async_wait_all()
 #endif
 }
 
+// Per-thread cp.async groups: commit closes the group of copies issued since the last commit,
+// wait_group<N> returns when at most N of the thread's most recent groups are still in flight.
+__device__ __forceinline__ void cp_async_commit()
+{
+#ifndef HUF_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group()
+{
+#ifndef HUF_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // Hint: bring the 128-byte line at p into L2 (no register, no stall).
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {

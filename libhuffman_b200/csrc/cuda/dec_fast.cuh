@@ -10,12 +10,21 @@
 //                  only (src/tree.c:410-413), codes of at most 32 bits.  Anything else --
 //                  foreign tree shapes, broken headers, zero-length blocks -- is left to
 //                  k_decode_slow, which implements the whole acceptance grammar.
-//   K5  k_decode   one CTA per eligible candidate, the block's payload processed in chunks:
-//                  (0) chunk staged in shared memory as big-endian words (coalesced 16-byte loads)
+//   K5  k_decode   one 256-thread CTA per eligible candidate (handed out dynamically, four
+//                  CTAs per SM), the block's payload processed in chunks:
+//                  (0) chunk staged in shared memory as big-endian words (coalesced 16-byte
+//                      loads, all of a thread's requests in flight together and issued before
+//                      the previous chunk is copied out)
 //                  (1) every thread warms up on the bits in front of its sub-block (Huffman
 //                      codes self-synchronise within ~20 code words), then decodes its sub-block
 //                      and WRITES the symbols into a private shared-memory region (4 symbols per
-//                      32-bit store): no symbol is decoded twice
+//                      32-bit store): no symbol is decoded twice.  The walk keeps three staged
+//                      words in registers (every word is loaded once), looks four code words up
+//                      per iteration through a 12-bit table behind the root bit whose 8 KB
+//                      aligned base is OR-ed into the index, and stores into regions that are
+//                      interleaved by thread (bank = thread: no conflicts).  Sub-blocks are sized
+//                      for the block's average code length; a region that runs full makes the
+//                      CTA repeat the chunk with the length that is safe for the shortest code
 //                  (2) verification: a thread's first code word must start where its
 //                      predecessor's last one ended.  A thread that did not synchronise decodes
 //                      its sub-block again from the proven position; rounds repeat until nothing
@@ -56,13 +65,13 @@ constexpr uint32_t kFastFlags = 0xc0u;
 // length, [31:16] number of terminals; [1] number of long-code records
 constexpr uint32_t kMetaFast = 1u;
 
-constexpr int kFT = 128;                  // threads per CTA
-constexpr int kRegWords = 56;             // words per thread region
+constexpr int kFT = 256;                  // threads per CTA (128 threads with sub-blocks twice as long: ~2 % slower)
+constexpr int kRegWords = 26;             // words per thread region
 constexpr int kRegCap = 4 * kRegWords;    // symbols a region can hold
 constexpr int kRegRow = kFT * 4;          // regions are interleaved: word c of thread t sits at
                                           // row c, column t -- the bank is the thread's, so region
                                           // stores and loads never conflict whatever c each lane is at
-constexpr int kMaxSubWords = 27;          // payload words per thread per chunk (odd)
+constexpr int kMaxSubWords = 13;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 // Dynamic shared memory of k_decode (the kernel has no static shared memory, so the block
@@ -73,7 +82,7 @@ constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (m
 //                              table index is OR-ed into the base
 //   [kFastRegOff, ...)         symbol regions, one per thread
 //   [kFastTailOff, kFastDyn)   FastTail: long-code records, re-speculation classes
-// kFastDyn + 1 KB is exactly a quarter of the 228 KB an SM offers: four CTAs per SM.
+// kFastDyn + 1 KB stays below a quarter of the 228 KB an SM offers: four CTAs per SM.
 constexpr int kFastLutOff = 15360;
 constexpr int kFastLutAlign = 2 * kLutSize;               // 8 KB
 constexpr int kFastRegOff = kFastLutOff + 2 * kLutSize;
@@ -267,13 +276,13 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
 
 struct FastSmall {
     uint32_t sub_end[kFT];
-    uint32_t pred[kFT];            // predicted true start of every sub-block
     uint32_t warp_tot[kFT / 32];
     uint32_t nlong;
     uint32_t redo;
     uint32_t fin_found;
     uint32_t fin_end;
     uint32_t total;
+    uint32_t ovf;                  // a region ran full: the chunk is repeated with safe sub-blocks
     unsigned long long next_j;
 };
 
@@ -281,6 +290,7 @@ struct FastTail {
     uint32_t long_code[kLongMax];  // left-aligned code words longer than the table reach, ascending
     uint32_t c_start[2][kFT];      // re-speculation: first code word of the primary / alternate
     uint32_t c_end[2][kFT];        // trajectory of every sub-block and where it leaves it
+    uint32_t pred[kFT];            // predicted true start of every sub-block
     uint16_t long_ent[kLongMax];   // length << 8 | symbol
 };
 
@@ -450,7 +460,7 @@ __device__ unsigned long long g_fast_prof[16];
 #define HUF_PROF_CNT(k)
 #endif
 
-__global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
+__global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
 {
 #ifdef HUF_EMU
     uint8_t *dyn = hufemu::dyn_smem();
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
             }
             if (tid == 0) {
                 sm.redo = 0;
+                sm.ovf = 0;
                 sm.nlong = nlong;
             }
             cta_sync();
@@ -565,9 +576,20 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
         uint64_t produced = 0, end_bit = 0;
         const uint64_t out0 = a.out_off[j];
         const bool can_write = !a.count_only && out0 + orig_len <= a.out_cap;
-        uint32_t sub_cap_w = min((uint32_t)kMaxSubWords, (kRegCap * min_len) / 32u);
-        if (!(sub_cap_w & 1)) sub_cap_w--;  // kRegCap / 32 = 7, so never below 7 (odd: the staged
-                                            // words of the threads of a warp start in different banks)
+        // Sub-block length.  Safe: even a run of the shortest code word cannot overfill a region.
+        // Speculative: sized for the block's AVERAGE code length (regions two thirds full), which
+        // is far longer for ordinary data; a region that does run full makes the CTA repeat the
+        // chunk with the safe length and keep it for the rest of the block.
+        uint32_t safe_cap_w = min((uint32_t)kMaxSubWords, (kRegCap * min_len) / 32u);
+        if (!(safe_cap_w & 1)) safe_cap_w--;  // kRegCap / 32 = 7, so never below 7 (odd: the staged
+                                              // words of the threads of a warp start in different banks)
+        uint32_t sub_cap_w = safe_cap_w;
+        if (use_guess) {
+            const uint64_t w = (uint64_t)(kRegCap * 2 / 3) * (guess_end - 8ull * pay0) / (32ull * orig_len);
+            uint32_t spec = (uint32_t)(w < (uint64_t)kMaxSubWords ? w : (uint64_t)kMaxSubWords);
+            if (!(spec & 1)) spec--;
+            if (spec > safe_cap_w && spec <= (uint32_t)kMaxSubWords) sub_cap_w = spec;
+        }
         // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
         uint32_t warm = 160;
         if (use_guess) {
@@ -720,21 +742,27 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     // `acc` (earliest lowest), so a group of four always leaves as one 32-bit
                     // store even after single steps have left the count unaligned.
                     saddr_t wp = reg_s;            // word the next store goes to
+                    const saddr_t wp_end = reg_s + (saddr_t)kRegWords * kRegRow;
+                    bool ovf = false;
                     uint32_t acc = 0, npend = 0;   // pending symbols
                     uint32_t sh = 32;              // 32 - 8 * npend
                     auto put = [&](uint32_t sy) {
                         acc = (acc >> 8) | (sy << 24);
                         npend++;
                         if (npend == 4) {
-                            sts_u32(wp, acc);
-                            wp += kRegRow;
+                            if (wp != wp_end) {
+                                sts_u32(wp, acc);
+                                wp += kRegRow;
+                            } else {
+                                ovf = true;
+                            }
                             npend = 0;
                         }
                         sh = 32 - 8 * npend;
                     };
                     BitWin b;
                     if (pos < my_hi) win_load(b, sw_s, pos);
-                    while (pos < my_hi) {
+                    while (pos < my_hi && !ovf) {
                         uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
                         const uint32_t np = fast_look4(b, lut_s, pos, e0, e1, e2, e3, h0, h1, h2, h3);
                         if (!(((e0 | e1 | e2 | e3) & kFastFlags) | ((h0 | h1 | h2 | h3) >> 31))) {
@@ -744,6 +772,10 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                             const uint32_t four = __byte_perm(lo2, hi2, 0x5410);
                             if (np <= my_hi) {
                                 // ... that all start inside my sub-block: one 32-bit store
+                                if (wp == wp_end) {
+                                    ovf = true;
+                                    break;
+                                }
                                 win_advance(b, sw_s, pos, np);
                                 pos = np;
                                 sts_u32(wp, __funnelshift_rc(acc, four, sh));  // pending bytes below, new ones above
@@ -781,13 +813,17 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                         }
                         if (pos < my_hi) win_load(b, sw_s, pos);
                     }
-                    if (npend) sts_u32(wp, acc >> sh);
+                    if (npend) {
+                        if (wp != wp_end) sts_u32(wp, acc >> sh); else ovf = true;
+                    }
+                    if (ovf) sm.ovf = 1;
                     cnt = (uint32_t)((wp - reg_s) / (uint32_t)kRegRow) * 4u + npend;
                     end = pos;
                     sm.sub_end[tid] = end;
                 }
                 if (round == 0) HUF_PROF(2);
                 cta_sync();
+                if (sm.ovf) break;  // (uniform: nobody walks again before the next barrier)
                 const uint32_t want = (tid == 0 || (uint32_t)tid >= nact) ? start : sm.sub_end[tid - 1];
                 walk = want != start;
                 const uint32_t had = start;  // what my region was decoded from
@@ -822,9 +858,9 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     cta_sync();
                     if (tid == 0) {
                         uint32_t cur = ft.c_end[0][0];  // thread 0 decoded from the proven start
-                        sm.pred[0] = ft.c_start[0][0];
+                        ft.pred[0] = ft.c_start[0][0];
                         for (uint32_t t = 1; t < nact; t++) {
-                            sm.pred[t] = cur;
+                            ft.pred[t] = cur;
                             if (cur == ft.c_start[0][t]) {
                                 cur = ft.c_end[0][t];
                             } else if (cur == ft.c_start[1][t]) {
@@ -836,10 +872,19 @@ __global__ void __launch_bounds__(kFT) k_decode(DecArgs a)
                     }
                     cta_sync();
                     if ((uint32_t)tid < nact) {
-                        start = sm.pred[tid];
+                        start = ft.pred[tid];
                         walk = start != had;
                     }
                 }
+            }
+            if (sm.ovf) {
+                // a region ran full under the speculative sub-block length: nothing of this
+                // chunk has left shared memory yet, so it is simply decoded again
+                cta_sync();
+                if (tid == 0) sm.ovf = 0;
+                sub_cap_w = safe_cap_w;
+                HUF_PROF(3);
+                continue;
             }
             HUF_PROF(3);
             // (3) symbol-count scan

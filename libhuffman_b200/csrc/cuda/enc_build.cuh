@@ -21,7 +21,7 @@
 
 namespace hufb200 {
 
-constexpr int kMergeDyn = 256 * 32 * 4;  // one u32 per merge node and lane
+constexpr int kMergeDyn = (256 + 16) * 32 * 4;  // one u32 per merge node and lane + the key ring
 
 // ------------------------------------------------------------------------------------------
 // K2a
@@ -113,8 +113,20 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
     // plus [nxt, made).
     uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0;
     uint32_t runw = 0;
-    uint32_t k0 = keys[0];  // n >= 1
-    uint32_t k1 = n > 1 ? keys[1] : kMax;
+    // The keys of a lane's block are a private global array (one sector per lane and load), so
+    // a load issued when its key is needed would put a full memory latency into every step of
+    // the chain.  Keys travel through a per-lane ring in shared memory instead, filled by
+    // asynchronous copies that are issued eight leaf picks before the key is looked at (one
+    // cp.async group per key; absent symbols sort to the end as kMax, so all 256 keys exist).
+    constexpr int kAhead = 8;
+    uint32_t *ring = nodev + 256 * 32 + lane;  // ring[(i & 15) * 32] = keys[i]
+#define KEY(i) ((i) < 256u ? ring[((i) & 15u) * 32] : kMax)
+#pragma unroll
+    for (int i = 0; i < kAhead; i++) {
+        cp_async4(&ring[i * 32], &keys[i]);
+        cp_async_commit();
+    }
+    (void)n;
     for (;;) {
         uint32_t pick0 = 0, pick1 = kNone16;
         uint32_t w0 = 0, w1 = 0, nl = 0;
@@ -130,6 +142,8 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
             }
             const bool has_i = top > head;
             const uint32_t ikey = has_i ? make_key<uint32_t>(runw, 255u + top) : kMax;
+            cp_async_wait_group<kAhead - 1>();  // the group of keys[li] has landed
+            const uint32_t k0 = KEY(li);
             if (ikey == kMax && k0 == kMax) break;  // nothing left (second pick only)
             uint32_t pick, pw, pl;
             if (ikey < k0) {
@@ -143,8 +157,8 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
                 pw = k0 >> 9;
                 pl = 1;
                 li++;
-                k0 = k1;
-                k1 = li + 1 < n ? keys[li + 1] : kMax;
+                if (li + kAhead - 1 < 256u) cp_async4(&ring[((li + kAhead - 1) & 15u) * 32], &keys[li + kAhead - 1]);
+                cp_async_commit();
             }
             if (s == 0) {
                 pick0 = pick;
@@ -168,6 +182,7 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
         if (got < 2) break;
     }
 #undef NODEV
+#undef KEY
 }
 
 // ------------------------------------------------------------------------------------------

@@ -286,6 +286,14 @@ inline uint32_t __ballot_sync(unsigned, int pred)
         return m;
     });
 }
+inline uint32_t __match_any_sync(unsigned, uint32_t v)
+{
+    return hufemu::warp_exchange(v, [&](uint64_t *x) {
+        uint32_t m = 0;
+        for (int l = 0; l < 32; l++) m |= (uint32_t)((uint32_t)x[l] == v) << l;
+        return m;
+    });
+}
 template <typename T>
 inline T __shfl_down_sync(unsigned, T v, unsigned d)
 {
