@@ -102,6 +102,11 @@ inline saddr_t saddr_or(saddr_t base, uint32_t off) { return base + off; }
 inline saddr_t saddr_pin(saddr_t a) { return a; }
 inline uint32_t lds_u16(saddr_t a) { return *reinterpret_cast<const uint16_t *>(a); }
 inline uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t *>(a); }
+// v = *a when pred is non-zero (predicated, no branch on the device)
+inline void lds_u32_if(uint32_t &v, saddr_t a, uint32_t pred)
+{
+    if (pred) v = *reinterpret_cast<const uint32_t *>(a);
+}
 inline void lds_u32x2(saddr_t a, uint32_t &w0, uint32_t &w1)
 {
     const uint32_t *p = reinterpret_cast<const uint32_t *>(a);
@@ -141,6 +146,10 @@ __device__ __forceinline__ uint32_t lds_u32(saddr_t a)
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
+}
+__device__ __forceinline__ void lds_u32_if(uint32_t &v, saddr_t a, uint32_t pred)
+{
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.shared.u32 %0, [%1]; }" : "+r"(v) : "r"(a), "r"(pred));
 }
 __device__ __forceinline__ void lds_u32x2(saddr_t a, uint32_t &w0, uint32_t &w1)
 {

@@ -66,7 +66,8 @@ constexpr uint32_t kFastFlags = 0xc0u;
 constexpr uint32_t kMetaFast = 1u;
 
 constexpr int kFT = 256;                  // threads per CTA (128 threads with sub-blocks twice as long: ~2 % slower)
-constexpr int kRegWords = 26;             // words per thread region
+constexpr int kRegWords = 25;             // words per thread region (+ one row behind them that
+                                          // takes the stores of a region that has run full)
 constexpr int kRegCap = 4 * kRegWords;    // symbols a region can hold
 constexpr int kRegRow = kFT * 4;          // regions are interleaved: word c of thread t sits at
                                           // row c, column t -- the bank is the thread's, so region
@@ -86,7 +87,7 @@ constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (m
 constexpr int kFastLutOff = 15360;
 constexpr int kFastLutAlign = 2 * kLutSize;               // 8 KB
 constexpr int kFastRegOff = kFastLutOff + 2 * kLutSize;
-constexpr int kFastTailOff = kFastRegOff + kRegWords * kRegRow;
+constexpr int kFastTailOff = kFastRegOff + (kRegWords + 1) * kRegRow;
 
 constexpr int kRespecMin = 2;             // threads still failing after one repair round: a ripple, re-speculate
 constexpr int kRespecStarts = 16;         // warm-up start offsets tried for the alternate trajectory
@@ -315,22 +316,37 @@ __device__ __forceinline__ void win_load(BitWin &b, saddr_t sw_s, uint32_t pos)
     lds_u32x3(sw_s + ((pos >> 5) << 2), b.w0, b.w1, b.w2);
 }
 
-// The walk moved from `pos` to `np` (at most two words further).
+// The walk moved from `pos` to `np` (at most two words further).  Branch-free: predicated
+// register moves and predicated loads of the one or two new words.
 __device__ __forceinline__ void win_advance(BitWin &b, saddr_t sw_s, uint32_t pos, uint32_t np)
 {
     const uint32_t adv = (np >> 5) - (pos >> 5);
-    if (adv) {
-        const saddr_t at = sw_s + ((np >> 5) << 2);
-        const uint32_t n2 = lds_u32(at + 8);
-        if (adv == 1) {
-            b.w0 = b.w1;
-            b.w1 = b.w2;
-        } else {
-            b.w0 = b.w2;
-            b.w1 = lds_u32(at + 4);
-        }
-        b.w2 = n2;
+    const saddr_t at = sw_s + ((np >> 5) << 2);
+#ifdef HUF_EMU
+    if (adv == 1) {
+        b.w0 = b.w1;
+        b.w1 = b.w2;
+        b.w2 = lds_u32(at + 8);
+    } else if (adv == 2) {
+        b.w0 = b.w2;
+        b.w1 = lds_u32(at + 4);
+        b.w2 = lds_u32(at + 8);
     }
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        "setp.ne.u32 p1, %4, 0;\n\t"
+        "setp.gt.u32 p2, %4, 1;\n\t"
+        "@p1 mov.u32 %0, %1;\n\t"
+        "@p1 mov.u32 %1, %2;\n\t"
+        "@p2 mov.u32 %0, %2;\n\t"
+        "@p2 ld.shared.u32 %1, [%3+4];\n\t"
+        "@p1 ld.shared.u32 %2, [%3+8];\n\t"
+        "}"
+        : "+r"(b.w0), "+r"(b.w1), "+r"(b.w2)
+        : "r"(at), "r"(adv));
+#endif
 }
 
 // Four consecutive table entries from `pos` on: the three window words are shifted into a
@@ -742,27 +758,24 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     // `acc` (earliest lowest), so a group of four always leaves as one 32-bit
                     // store even after single steps have left the count unaligned.
                     saddr_t wp = reg_s;            // word the next store goes to
+                    // a full region keeps storing into the row behind it (no branch in the loop);
+                    // reaching that row is what reports the overflow afterwards
                     const saddr_t wp_end = reg_s + (saddr_t)kRegWords * kRegRow;
-                    bool ovf = false;
                     uint32_t acc = 0, npend = 0;   // pending symbols
                     uint32_t sh = 32;              // 32 - 8 * npend
                     auto put = [&](uint32_t sy) {
                         acc = (acc >> 8) | (sy << 24);
                         npend++;
                         if (npend == 4) {
-                            if (wp != wp_end) {
-                                sts_u32(wp, acc);
-                                wp += kRegRow;
-                            } else {
-                                ovf = true;
-                            }
+                            sts_u32(wp, acc);
+                            wp = min(wp + (saddr_t)kRegRow, wp_end);
                             npend = 0;
                         }
                         sh = 32 - 8 * npend;
                     };
                     BitWin b;
                     if (pos < my_hi) win_load(b, sw_s, pos);
-                    while (pos < my_hi && !ovf) {
+                    while (pos < my_hi) {
                         uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
                         const uint32_t np = fast_look4(b, lut_s, pos, e0, e1, e2, e3, h0, h1, h2, h3);
                         if (!(((e0 | e1 | e2 | e3) & kFastFlags) | ((h0 | h1 | h2 | h3) >> 31))) {
@@ -772,15 +785,11 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                             const uint32_t four = __byte_perm(lo2, hi2, 0x5410);
                             if (np <= my_hi) {
                                 // ... that all start inside my sub-block: one 32-bit store
-                                if (wp == wp_end) {
-                                    ovf = true;
-                                    break;
-                                }
                                 win_advance(b, sw_s, pos, np);
                                 pos = np;
                                 sts_u32(wp, __funnelshift_rc(acc, four, sh));  // pending bytes below, new ones above
                                 acc = four;                                    // its top bytes are the new pending ones
-                                wp += kRegRow;
+                                wp = min(wp + (saddr_t)kRegRow, wp_end);
                                 continue;
                             }
                             // the sub-block ends among them: the first is mine, the others may be
@@ -813,10 +822,8 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                         }
                         if (pos < my_hi) win_load(b, sw_s, pos);
                     }
-                    if (npend) {
-                        if (wp != wp_end) sts_u32(wp, acc >> sh); else ovf = true;
-                    }
-                    if (ovf) sm.ovf = 1;
+                    if (npend) sts_u32(wp, acc >> sh);
+                    if (wp == wp_end) sm.ovf = 1;
                     cnt = (uint32_t)((wp - reg_s) / (uint32_t)kRegRow) * 4u + npend;
                     end = pos;
                     sm.sub_end[tid] = end;

@@ -31,9 +31,9 @@ src = subprocess.run(["ncu", "-i", str(G / "prof_dec.ncu-rep"), "--page", "sourc
                       "--kernel-name", "k_decode"], capture_output=True, text=True).stdout
 Path("/tmp/src_dec.csv").write_text(src)
 phase = subprocess.run([sys.executable, str(ROOT / "scripts" / "ncu_phase.py"), "/tmp/src_dec.csv",
-                        str(ROOT / "libhuffman_b200/csrc/cuda/dec_fast.cuh"), "look:fast_look(const uint32_t *sw",
+                        str(ROOT / "libhuffman_b200/csrc/cuda/dec_fast.cuh"), "win:The three staged words from",
                         "look4:Four consecutive table entries", "step:One exact decode step", "ctasync:CTA barrier behind divergent",
-                        "smemcopy:Copy n bytes between", "kernel_head:k_decode(DecArgs a)", "lutfill:lookup table from the ordered",
+                        "regcopy:Copy symbols [s0, s0 + n)", "kernel_head:k_decode(DecArgs a)", "lutfill:lookup table from the ordered",
                         "chunkhead:// ---- chunk loop", "stage:(0) stage the chunk", "warm:(1) warm-up in front",
                         "walk+verify:(1b) decode my sub-block", "scan:(3) symbol-count scan", "compact:(4) compaction into",
                         "tail:if (status == kOk && end_bit"], capture_output=True, text=True).stdout
