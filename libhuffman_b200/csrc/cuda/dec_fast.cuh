@@ -349,6 +349,21 @@ __device__ __forceinline__ void win_advance(BitWin &b, saddr_t sw_s, uint32_t po
 #endif
 }
 
+// Length field for the blind walk: the entry, or 1 when the window starts on a set root bit
+// (two instructions: arithmetic shift + one three-input logic op).
+__device__ __forceinline__ uint32_t blind_len(uint32_t e, uint32_t h)
+{
+#ifdef HUF_EMU
+    const uint32_t m = (uint32_t)((int32_t)h >> 31);
+    return (e & ~m) | (m & 1u);
+#else
+    uint32_t m, l;
+    asm("shr.s32 %0, %1, 31;" : "=r"(m) : "r"(h));
+    asm("lop3.b32 %0, %1, %2, 1, 0xb8;" : "=r"(l) : "r"(e), "r"(m));  // (e & ~m) | (m & 1)
+    return l;
+#endif
+}
+
 // Four consecutive table entries from `pos` on: the three window words are shifted into a
 // 64-bit left-aligned bit buffer that is then shifted by every code length (4 x 13 bits fit; the
 // shifter takes the low five bits of an entry, i.e. its length, 1 for the special kinds).
@@ -600,18 +615,20 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
         if (!(safe_cap_w & 1)) safe_cap_w--;  // kRegCap / 32 = 7, so never below 7 (odd: the staged
                                               // words of the threads of a warp start in different banks)
         uint32_t sub_cap_w = safe_cap_w;
-        if (use_guess) {
-            const uint64_t w = (uint64_t)(kRegCap * 2 / 3) * (guess_end - 8ull * pay0) / (32ull * orig_len);
-            uint32_t spec = (uint32_t)(w < (uint64_t)kMaxSubWords ? w : (uint64_t)kMaxSubWords);
-            if (!(spec & 1)) spec--;
-            if (spec > safe_cap_w && spec <= (uint32_t)kMaxSubWords) sub_cap_w = spec;
-        }
-        // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
+        // (sizes are heuristics: single-precision arithmetic is exact enough and much cheaper
+        // than 64-bit integer division)
         uint32_t warm = 160;
         if (use_guess) {
-            const uint64_t w = 20ull * (guess_end - 8ull * pay0) / orig_len;
-            warm = (uint32_t)(w < 64 ? 64 : (w > 320 ? 320 : w));
+            const float avg_bits = (float)(guess_end - 8ull * pay0) / (float)orig_len;  // per code word
+            const float w = (float)(kRegCap * 2 / 3) * avg_bits * (1.0f / 32.0f);
+            uint32_t spec = w < (float)kMaxSubWords ? (uint32_t)w : (uint32_t)kMaxSubWords;
+            if (!(spec & 1)) spec--;
+            if (spec > safe_cap_w && spec <= (uint32_t)kMaxSubWords) sub_cap_w = spec;
+            // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
+            const float wb = 20.0f * avg_bits;
+            warm = wb < 64.0f ? 64u : (wb > 320.0f ? 320u : (uint32_t)wb);
         }
+        float inv_chunk_cap = 1.0f / (float)((uint32_t)kFT * 32u * sub_cap_w);
         uint32_t status = kOk;
         // staged 16-byte pieces of a thread (piece tid + q * kFT of the chunk), loaded with all
         // requests in flight together; the next chunk's are requested before the current chunk
@@ -659,10 +676,11 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             // span beyond 4 Gbit only needs the right order of magnitude)
             const uint64_t span64 = limit - (8ull * base16 + A);
             const uint32_t span = span64 > 0xf0000000ull ? 0xf0000000u : (uint32_t)span64;
-            const uint32_t chunk_cap = (uint32_t)kFT * 32u * sub_cap_w;
-            const uint32_t nch = (span + chunk_cap - 1) / chunk_cap;
-            const uint32_t per_word = nch * (uint32_t)kFT * 32u;
-            uint32_t subw = (span + per_word - 1) / per_word;
+            // (any odd length between 7 and sub_cap_w words is valid: the divisions only have
+            // to be about right, so they are single-precision multiplications)
+            const float fspan = (float)span;
+            const uint32_t nch = (uint32_t)(fspan * inv_chunk_cap) + 1u;
+            uint32_t subw = (uint32_t)(fspan / (float)(nch * (uint32_t)kFT * 32u)) + 1u;
             subw |= 1u;
             if (subw < 7) subw = 7;
             if (subw > sub_cap_w) subw = sub_cap_w;
@@ -671,7 +689,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             const uint64_t cov64 = (uint64_t)A + (uint64_t)kFT * sub;
             const uint32_t cover = (uint32_t)(cov64 < lim_rel ? cov64 : lim_rel);
             // threads whose sub-block starts inside the covered bits take part in this chunk
-            const uint32_t nact = (cover - A + sub - 1) / sub;
+            const uint32_t nact = cov64 <= lim_rel ? (uint32_t)kFT : (cover - A + sub - 1) / sub;
 
             // (0) stage the chunk: 16-byte loads, bytes past `avail` read as zero; the lines of
             // the chunk behind it are requested into L2 meanwhile
@@ -712,19 +730,15 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     // (mask = all ones under a set root bit, computed beside the table load)
                     const uint32_t h0 = __funnelshift_l(b.w1, b.w0, p);
                     uint32_t lo = __funnelshift_l(b.w2, b.w1, p);
-                    uint32_t m = (uint32_t)((int32_t)h0 >> 31);
-                    const uint32_t l0 = (lds_u16(saddr_or(lut_s, fast_idx(h0))) & ~m) | (m & 1u);
+                    const uint32_t l0 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h0))), h0);
                     const uint32_t h1 = __funnelshift_l(lo, h0, l0);
                     lo = __funnelshift_l(0u, lo, l0);
-                    m = (uint32_t)((int32_t)h1 >> 31);
-                    const uint32_t l1 = (lds_u16(saddr_or(lut_s, fast_idx(h1))) & ~m) | (m & 1u);
+                    const uint32_t l1 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h1))), h1);
                     const uint32_t h2 = __funnelshift_l(lo, h1, l1);
                     lo = __funnelshift_l(0u, lo, l1);
-                    m = (uint32_t)((int32_t)h2 >> 31);
-                    const uint32_t l2 = (lds_u16(saddr_or(lut_s, fast_idx(h2))) & ~m) | (m & 1u);
+                    const uint32_t l2 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h2))), h2);
                     const uint32_t h3 = __funnelshift_l(lo, h2, l2);
-                    m = (uint32_t)((int32_t)h3 >> 31);
-                    const uint32_t l3 = (lds_u16(saddr_or(lut_s, fast_idx(h3))) & ~m) | (m & 1u);
+                    const uint32_t l3 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h3))), h3);
                     const uint32_t np = p + ((l0 + l1 + l2 + l3) & 0x3fu);
                     if (np < limit) {  // four steps at a time while the fifth starts in front of the limit
                         win_advance(b, sw_s, p, np);
@@ -890,6 +904,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                 cta_sync();
                 if (tid == 0) sm.ovf = 0;
                 sub_cap_w = safe_cap_w;
+                inv_chunk_cap = 1.0f / (float)((uint32_t)kFT * 32u * sub_cap_w);
                 HUF_PROF(3);
                 continue;
             }
