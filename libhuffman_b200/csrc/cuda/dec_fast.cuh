@@ -442,11 +442,18 @@ __device__ __forceinline__ void cta_sync()
 // whole words assembled with one funnel shift each, then up to three bytes.
 __device__ __forceinline__ void region_copy(uint8_t *dst, const uint32_t *regw, uint32_t s0, uint32_t n)
 {
-    auto sym = [&](uint32_t i) -> uint8_t { return (uint8_t)(regw[(i >> 2) * kFT] >> (8 * (i & 3))); };
+    // four symbols from symbol i on: two region words and one funnel shift
+    auto four_at = [&](uint32_t i) -> uint32_t {
+        const uint32_t *p = regw + (i >> 2) * kFT;
+        return __funnelshift_r(p[0], p[kFT], (i & 3) * 8);
+    };
     const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
-    if (head > 0) dst[0] = sym(s0);
-    if (head > 1) dst[1] = sym(s0 + 1);
-    if (head > 2) dst[2] = sym(s0 + 2);
+    if (head) {
+        const uint32_t hw = four_at(s0);
+        dst[0] = (uint8_t)hw;
+        if (head > 1) dst[1] = (uint8_t)(hw >> 8);
+        if (head > 2) dst[2] = (uint8_t)(hw >> 16);
+    }
     const uint32_t sb = s0 + head;
     const uint32_t sh = (sb & 3) * 8;
     const uint32_t *__restrict__ sp = regw + (sb >> 2) * kFT;
@@ -469,9 +476,12 @@ __device__ __forceinline__ void region_copy(uint8_t *dst, const uint32_t *regw, 
         prev = a1;
     }
     const uint32_t done = head + 4 * nw;
-    if (done < n) dst[done] = sym(s0 + done);
-    if (done + 1 < n) dst[done + 1] = sym(s0 + done + 1);
-    if (done + 2 < n) dst[done + 2] = sym(s0 + done + 2);
+    if (done < n) {
+        const uint32_t tw = four_at(s0 + done);
+        dst[done] = (uint8_t)tw;
+        if (done + 1 < n) dst[done + 1] = (uint8_t)(tw >> 8);
+        if (done + 2 < n) dst[done + 2] = (uint8_t)(tw >> 16);
+    }
 }
 
 // Phase timing of thread 0 of every CTA (debug builds with -DHUF_PHASE_PROF only): cycles per
@@ -617,16 +627,19 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
         uint32_t sub_cap_w = safe_cap_w;
         // (sizes are heuristics: single-precision arithmetic is exact enough and much cheaper
         // than 64-bit integer division)
-        uint32_t warm = 160;
+        uint32_t warm = 192;
         if (use_guess) {
             const float avg_bits = (float)(guess_end - 8ull * pay0) / (float)orig_len;  // per code word
             const float w = (float)(kRegCap * 2 / 3) * avg_bits * (1.0f / 32.0f);
             uint32_t spec = w < (float)kMaxSubWords ? (uint32_t)w : (uint32_t)kMaxSubWords;
             if (!(spec & 1)) spec--;
             if (spec > safe_cap_w && spec <= (uint32_t)kMaxSubWords) sub_cap_w = spec;
-            // warm-up distance: ~20 average code words (measured 99.9 % self-synchronisation point)
-            const float wb = 20.0f * avg_bits;
-            warm = wb < 64.0f ? 64u : (wb > 320.0f ? 320u : (uint32_t)wb);
+            // warm-up distance: ~24 average code words.  A Zipf(1.1) code leaves 0.13 % of the
+            // walks unsynchronised after 20 code words and halves that every 2.5 more; with 256
+            // sub-blocks per chunk a failed walk (one repair round for the whole CTA) costs more
+            // than the four extra code words of everybody
+            const float wb = 24.0f * avg_bits;
+            warm = wb < 64.0f ? 64u : (wb > 384.0f ? 384u : (uint32_t)wb);
         }
         float inv_chunk_cap = 1.0f / (float)((uint32_t)kFT * 32u * sub_cap_w);
         uint32_t status = kOk;
@@ -639,6 +652,15 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
         uint64_t pre_base = 0;
         uint32_t pre_n16 = 0, cur_n16 = 0;
         auto stage_issue = [&](uint64_t from16, uint32_t n16) {
+            if (from16 + 16ull * n16 <= a.avail) {
+                // the whole chunk is readable (every chunk but the last of a stream)
+                const uint8_t *src = a.in + from16 + 16ull * (uint32_t)tid;
+#pragma unroll
+                for (int q = 0; q < kStageIter; q++) {
+                    if ((uint32_t)tid + (uint32_t)q * kFT < n16) v[q] = ld_stream_u4(src + 16 * q * kFT);
+                }
+                return;
+            }
 #pragma unroll
             for (int q = 0; q < kStageIter; q++) {
                 const uint32_t c = (uint32_t)tid + (uint32_t)q * kFT;
@@ -953,7 +975,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             if (!fin_found) {
                 // the block goes on: request the next chunk's payload (same length as this one's)
                 pre_base = ((8ull * base16 + sm.sub_end[nact - 1]) >> 3) & ~uint64_t(15);
-                pre_n16 = cur_n16;
+                pre_n16 = min(cur_n16 + 2u, (uint32_t)(kFastStage / 16));  // (its start skew may differ)
                 stage_issue(pre_base, pre_n16);
                 pre_ok = true;
             }
