@@ -10,7 +10,7 @@
 //                  only (src/tree.c:410-413), codes of at most 32 bits.  Anything else --
 //                  foreign tree shapes, broken headers, zero-length blocks -- is left to
 //                  k_decode_slow, which implements the whole acceptance grammar.
-//   K5  k_decode   one 256-thread CTA per eligible candidate (handed out dynamically, four
+//   K5  k_decode   one 128-thread CTA per eligible candidate (handed out dynamically, four
 //                  CTAs per SM), the block's payload processed in chunks:
 //                  (0) chunk staged in shared memory as big-endian words (coalesced 16-byte
 //                      loads, all of a thread's requests in flight together and issued before
@@ -65,14 +65,16 @@ constexpr uint32_t kFastFlags = 0xc0u;
 // length, [31:16] number of terminals; [1] number of long-code records
 constexpr uint32_t kMetaFast = 1u;
 
-constexpr int kFT = 256;                  // threads per CTA (128 threads with sub-blocks twice as long: ~2 % slower)
-constexpr int kRegWords = 25;             // words per thread region (+ one row behind them that
+constexpr int kFT = 128;                  // threads per CTA.  256 threads with sub-blocks half as long (kRegWords 25,
+                                          // kMaxSubWords 13) measure within 2-4 % either way: Zipf and Fibonacci
+                                          // shapes prefer 128, uniform / text / geometric prefer 256
+constexpr int kRegWords = 51;             // words per thread region (+ one row behind them that
                                           // takes the stores of a region that has run full)
 constexpr int kRegCap = 4 * kRegWords;    // symbols a region can hold
 constexpr int kRegRow = kFT * 4;          // regions are interleaved: word c of thread t sits at
                                           // row c, column t -- the bank is the thread's, so region
                                           // stores and loads never conflict whatever c each lane is at
-constexpr int kMaxSubWords = 13;          // payload words per thread per chunk (odd)
+constexpr int kMaxSubWords = 27;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 // Dynamic shared memory of k_decode (the kernel has no static shared memory, so the block
