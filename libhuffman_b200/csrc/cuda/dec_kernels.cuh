@@ -163,19 +163,26 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
                 // tree[0] high byte (offsets 11+4j .. 14+4j) must be 0x01 and the tree_len high
                 // byte (offsets 9+4j .. 12+4j) at most 0x04: 1 in 13000 random offsets, so the
                 // per-offset bit mask is only assembled when some byte lane survived
-                uint32_t eq[4];
+                // Cheap test first: z has a zero byte wherever byte o+11 is 0x01 and byte o+9 is
+                // below 8; the borrow trick flags every such byte (and, harmlessly, sometimes
+                // the byte above one).  The exact per-offset masks are only built for a lane
+                // that the cheap test did not clear.
+                uint32_t any = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t w11 = __funnelshift_r(d[2 + j], d[3 + j], 24);
                     const uint32_t w9 = __funnelshift_r(d[2 + j], d[3 + j], 8);
-                    eq[j] = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
+                    const uint32_t z = (w11 ^ 0x01010101u) | (w9 & 0xf8f8f8f8u);
+                    any |= (z - 0x01010101u) & ~z;
                 }
                 uint32_t pre = 0;
-                if (eq[0] | eq[1] | eq[2] | eq[3]) {
+                if (any & 0x80808080u) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        pre |= ((eq[j] & 1u) | ((eq[j] >> 7) & 2u) | ((eq[j] >> 14) & 4u) | ((eq[j] >> 21) & 8u))
-                               << (4 * j);
+                        const uint32_t w11 = __funnelshift_r(d[2 + j], d[3 + j], 24);
+                        const uint32_t w9 = __funnelshift_r(d[2 + j], d[3 + j], 8);
+                        const uint32_t eq = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
+                        pre |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * j);
                     }
                 }
                 while (pre) {
