@@ -135,27 +135,27 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
     const uint64_t in_aligned = a.avail & ~uint64_t(15);  // bytes readable with 16-byte loads
     for (uint32_t it0 = 0; it0 < kFindChunk / 512; it0 += 4) {
         if (c0 + (uint64_t)it0 * 512 >= lim) break;  // warp-uniform: nothing left in this chunk
-        // four independent 16-byte loads in flight per lane
-        uint4 v[4];
+        // four independent 16-byte loads in flight per lane; lane 0 also fetches the 16 bytes
+        // behind the fourth row (what lane 31 needs to look past its own bytes there)
+        uint4 v[5];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 5; u++) {
             const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;
             v[u] = make_uint4(0, 0, 0, 0);
-            if (vec_ok && (c0 & 15) == 0 && o0 + 16 <= in_aligned) v[u] = ld_stream_u4(a.in + o0);
+            if ((u < 4 || lane == 0) && vec_ok && (c0 & 15) == 0 && o0 + 16 <= in_aligned)
+                v[u] = ld_stream_u4(a.in + o0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
         const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;  // offsets o0 .. o0+15
         uint32_t mask = 0;                                               // bit i: o0+i is a candidate
-        // the 16 bytes that follow come from the next lane; lane 31 fetches them itself
-        uint32_t n0 = __shfl_down_sync(kFull, v[u].x, 1);
-        uint32_t n1 = __shfl_down_sync(kFull, v[u].y, 1);
-        uint32_t n2 = __shfl_down_sync(kFull, v[u].z, 1);
+        // the 16 bytes that follow come from the next lane; lane 31's are lane 0's of the next
+        // row (already in registers): lane 0 offers that row to the rotating shuffle
+        const int nl = (lane + 1) & 31;
+        const uint32_t n0 = __shfl_sync(kFull, lane == 0 ? v[u + 1].x : v[u].x, nl);
+        const uint32_t n1 = __shfl_sync(kFull, lane == 0 ? v[u + 1].y : v[u].y, nl);
+        const uint32_t n2 = __shfl_sync(kFull, lane == 0 ? v[u + 1].z : v[u].z, nl);
         const bool fast = vec_ok && (c0 & 15) == 0 && o0 + 32 <= in_aligned;
-        if (lane == 31 && fast) {
-            const uint4 nx = ld_stream_u4(a.in + o0 + 16);
-            n0 = nx.x; n1 = nx.y; n2 = nx.z;
-        }
         if (o0 < lim) {
             // bytes o0+11 .. o0+26 decide the pre-filter
             if (fast) {
