@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #ifndef HUF_EMU  // tests/emu/cuda_emu.h stands in for the CUDA headers in the CPU test lane
 #include <cuda_runtime.h>
 #endif
@@ -168,6 +169,59 @@ __device__ __forceinline__ void sts_u32(saddr_t a, uint32_t v)
 __device__ __forceinline__ void sts_u8(saddr_t a, uint32_t v)
 {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+#endif
+
+// Bulk asynchronous copy global -> shared by the TMA unit (cp.async.bulk, SASS UBLKCP): one
+// thread issues one instruction for the whole range, the bytes land without any register or
+// load/store-unit traffic of the CTA, and an mbarrier in shared memory counts them in.
+// Addresses and size are multiples of 16.  (tests/emu: a plain copy at request time.)
+#ifdef HUF_EMU
+inline void mbar_init(void *, uint32_t) {}
+inline void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, void *)
+{
+    memcpy(smem_dst, gsrc, bytes);
+}
+inline void mbar_wait(void *, uint32_t) {}
+inline void fence_async_proxy() {}
+#else
+__device__ __forceinline__ void mbar_init(void *mbar, uint32_t count)
+{
+    const uint32_t m = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(m), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// Orders the CTA's earlier generic-proxy accesses of shared memory before later writes of the
+// async proxy (the TMA unit) to the same bytes.
+__device__ __forceinline__ void fence_async_proxy()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// One thread: expect `bytes` on the barrier and start the copy.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, void *mbar)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const uint32_t m = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(m)
+                 : "memory");
+}
+// Every waiting thread: returns when the phase with the given parity has completed.
+__device__ __forceinline__ void mbar_wait(void *mbar, uint32_t parity)
+{
+    const uint32_t m = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "HUF_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra HUF_MBAR_DONE;\n\t"
+        "bra HUF_MBAR_WAIT;\n\t"
+        "HUF_MBAR_DONE:\n\t"
+        "}" ::"r"(m),
+        "r"(parity)
+        : "memory");
 }
 #endif
 

@@ -287,6 +287,7 @@ struct FastSmall {
     uint32_t total;
     uint32_t ovf;                  // a region ran full: the chunk is repeated with safe sub-blocks
     unsigned long long next_j;
+    unsigned long long mbar;       // mbarrier of the bulk copy that stages the payload
 };
 
 struct FastTail {
@@ -313,9 +314,13 @@ struct BitWin {
     uint32_t w0, w1, w2;
 };
 
+// (the stage holds the stream bytes as they are; a word becomes MSB-first bits by a byte swap)
 __device__ __forceinline__ void win_load(BitWin &b, saddr_t sw_s, uint32_t pos)
 {
     lds_u32x3(sw_s + ((pos >> 5) << 2), b.w0, b.w1, b.w2);
+    b.w0 = bswap32(b.w0);
+    b.w1 = bswap32(b.w1);
+    b.w2 = bswap32(b.w2);
 }
 
 // The walk moved from `pos` to `np` (at most two words further).  Branch-free: predicated
@@ -328,11 +333,11 @@ __device__ __forceinline__ void win_advance(BitWin &b, saddr_t sw_s, uint32_t po
     if (adv == 1) {
         b.w0 = b.w1;
         b.w1 = b.w2;
-        b.w2 = lds_u32(at + 8);
+        b.w2 = bswap32(lds_u32(at + 8));
     } else if (adv == 2) {
         b.w0 = b.w2;
-        b.w1 = lds_u32(at + 4);
-        b.w2 = lds_u32(at + 8);
+        b.w1 = bswap32(lds_u32(at + 4));
+        b.w2 = bswap32(lds_u32(at + 8));
     }
 #else
     asm volatile(
@@ -345,6 +350,8 @@ __device__ __forceinline__ void win_advance(BitWin &b, saddr_t sw_s, uint32_t po
         "@p2 mov.u32 %0, %2;\n\t"
         "@p2 ld.shared.u32 %1, [%3+4];\n\t"
         "@p1 ld.shared.u32 %2, [%3+8];\n\t"
+        "@p2 prmt.b32 %1, %1, 0, 0x0123;\n\t"
+        "@p1 prmt.b32 %2, %2, 0, 0x0123;\n\t"
         "}"
         : "+r"(b.w0), "+r"(b.w1), "+r"(b.w2)
         : "r"(at), "r"(adv));
@@ -403,7 +410,7 @@ __device__ __noinline__ uint64_t fast_step(saddr_t sw_s, saddr_t lut_s, const Fa
 {
     uint32_t w0, w1;
     lds_u32x2(sw_s + ((pos >> 5) << 2), w0, w1);
-    const uint32_t win = __funnelshift_l(w1, w0, pos);
+    const uint32_t win = __funnelshift_l(bswap32(w1), bswap32(w0), pos);
     const uint32_t e = lds_u16(saddr_or(lut_s, fast_idx(win)));
     const uint32_t root = win >> 31;
     if (!((e & kFastFlags) | root)) {
@@ -514,7 +521,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
     FastTail &ft = *reinterpret_cast<FastTail *>(dyn + kFastTailOff);
     const int tid = threadIdx.x;
 #ifdef HUF_PHASE_PROF
-    unsigned long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long pt = clock64();
 #endif
     const uint64_t ncand = a.result[0];
@@ -524,6 +531,10 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
     const uint32_t *regw = reinterpret_cast<const uint32_t *>(regions) + tid;  // my region: regw[c * kFT]
     const saddr_t sw_s = saddr_pin(smem_addr(sw)), lut_s = saddr_pin(smem_addr(lut));
     const saddr_t reg_s = saddr_pin(smem_addr(regw));  // first word of my region
+    uint32_t tma_phase = 0;    // parity of the staging barrier's next phase
+    bool tma_pending = false;  // a bulk copy into the stage buffer is in flight ...
+    uint64_t tma_base = 0;     // ... from this stream offset
+    if (tid == 0) mbar_init(&sm.mbar, 1);
 #ifndef HUF_EMU
     if (lut_s & (uint32_t)(kFastLutAlign - 1)) __trap();  // the table base is OR-ed into its index
 #endif
@@ -563,6 +574,31 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             if (noff < a.avail) prefetch_l2(a.in + noff);
             if (tid < 26) prefetch_l2(a.terms + (j + gridDim.x) * kTermStride + 32 * tid);
         }
+
+        // Staging.  The payload window of a chunk (kFastStage bytes from the 16-byte aligned
+        // `base16`) is brought in by ONE bulk copy of the TMA unit, requested by thread 0 as soon
+        // as the stage buffer is free and the window's start is known -- at the start of a block
+        // and behind the copy-out of every chunk -- so it flies during the table build and the
+        // chunk planning; everybody waits on its mbarrier at the top of the chunk.  Only a
+        // window that reaches past the readable bytes (the last chunks of a stream) is loaded
+        // with ordinary 16-byte loads, zero-filled behind `avail`.
+        auto stage_request = [&](uint64_t from16) {
+            tma_pending = from16 + (uint64_t)kFastStage <= a.avail;
+            tma_base = from16;
+            if (tma_pending && tid == 0) {
+                fence_async_proxy();  // the compaction window was written through the generic proxy
+                tma_load_1d(sw, a.in + from16, (uint32_t)kFastStage, &sm.mbar);
+            }
+#ifdef HUF_EMU
+            cta_sync();  // the emulator copies at request time: this stands in for the mbarrier wait
+#endif
+        };
+        auto stage_wait = [&]() {
+            mbar_wait(&sm.mbar, tma_phase);
+            tma_phase ^= 1u;
+            tma_pending = false;
+        };
+        stage_request(pay0 & ~uint64_t(15));  // the first chunk's window lands during the table build
 
         // ---- lookup table from the ordered terminal list: every thread fills 16 entries
         {
@@ -645,43 +681,6 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
         }
         float inv_chunk_cap = 1.0f / (float)((uint32_t)kFT * 32u * sub_cap_w);
         uint32_t status = kOk;
-        // staged 16-byte pieces of a thread (piece tid + q * kFT of the chunk), loaded with all
-        // requests in flight together; the next chunk's are requested before the current chunk
-        // is copied out, so their latency hides behind the copy-out
-        constexpr int kStageIter = (kFastStage / 16 + kFT - 1) / kFT;
-        uint4 v[kStageIter];
-        bool pre_ok = false;
-        uint64_t pre_base = 0;
-        uint32_t pre_n16 = 0, cur_n16 = 0;
-        auto stage_issue = [&](uint64_t from16, uint32_t n16) {
-            if (from16 + 16ull * n16 <= a.avail) {
-                // the whole chunk is readable (every chunk but the last of a stream)
-                const uint8_t *src = a.in + from16 + 16ull * (uint32_t)tid;
-#pragma unroll
-                for (int q = 0; q < kStageIter; q++) {
-                    if ((uint32_t)tid + (uint32_t)q * kFT < n16) v[q] = ld_stream_u4(src + 16 * q * kFT);
-                }
-                return;
-            }
-#pragma unroll
-            for (int q = 0; q < kStageIter; q++) {
-                const uint32_t c = (uint32_t)tid + (uint32_t)q * kFT;
-                const uint64_t byte = from16 + 16ull * c;
-                v[q] = make_uint4(0, 0, 0, 0);
-                if (c < n16) {
-                    if (byte + 16 <= a.avail) {
-                        v[q] = ld_stream_u4(a.in + byte);
-                    } else if (byte < a.avail) {
-                        uint32_t w[4] = {0, 0, 0, 0};
-                        for (int r = 0; r < 16; r++) {
-                            if (byte + r < a.avail) w[r >> 2] |= (uint32_t)a.in[byte + r] << (8 * (r & 3));
-                        }
-                        v[q] = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-            }
-        };
-
         for (;;) {
             HUF_PROF_CNT(7);
             const uint64_t limit = use_guess ? guess_end : room_end;
@@ -720,22 +719,28 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             {
                 const uint64_t nxt = base16 + ((cover + 7) >> 3) + 128ull * (uint32_t)tid;
                 if (nxt < a.avail && 128u * (uint32_t)tid < (kFT * sub >> 3) + 256u) prefetch_l2(a.in + nxt);
-                const uint32_t n16 = ((cover + 7) >> 3) / 16 + 2;
-                // the loads were issued in front of the previous chunk's copy-out when it
-                // predicted this chunk (same base, at least as long); otherwise they are now
-                if (!(pre_ok && pre_base == base16 && pre_n16 >= n16)) stage_issue(base16, n16);
-                pre_ok = false;
-                cur_n16 = n16;
-#pragma unroll
-                for (int q = 0; q < kStageIter; q++) {
-                    const uint32_t c = (uint32_t)tid + (uint32_t)q * kFT;
-                    if (c < n16) {
-                        reinterpret_cast<uint4 *>(sw)[c] =
-                            make_uint4(bswap32(v[q].x), bswap32(v[q].y), bswap32(v[q].z), bswap32(v[q].w));
+                if (tma_pending && tma_base == base16) {
+                    stage_wait();  // every thread sees the bytes once the barrier's phase is over
+                } else {
+                    if (tma_pending) stage_wait();  // (a window nobody wants: let it land first)
+                    const uint32_t n16 = ((cover + 7) >> 3) / 16 + 2;
+                    for (uint32_t c = tid; c < n16; c += kFT) {
+                        const uint64_t byte = base16 + 16ull * c;
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (byte + 16 <= a.avail) {
+                            v = ld_stream_u4(a.in + byte);
+                        } else if (byte < a.avail) {
+                            uint32_t w[4] = {0, 0, 0, 0};
+                            for (int r = 0; r < 16; r++) {
+                                if (byte + r < a.avail) w[r >> 2] |= (uint32_t)a.in[byte + r] << (8 * (r & 3));
+                            }
+                            v = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                        reinterpret_cast<uint4 *>(sw)[c] = v;
                     }
+                    cta_sync();
                 }
             }
-            cta_sync();
             HUF_PROF(1);
 
             // (1) warm-up in front of my sub-block, then decode it into my region
@@ -786,11 +791,16 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             // its end may move, the check repeats until nothing changes.
             uint32_t start = pos;  // first code word of mine (speculative unless tid == 0)
             uint32_t end = pos;
+            uint32_t chk_pos = pos, chk_cnt = 0;  // start of my last look-up group, symbols before it
+            bool chk_dead = false;                // a dead step in front of it
             bool walk = true;
             for (int round = 0; round <= kFT; round++) {
                 if (walk) {
                     pos = start;
                     last_dead = kNone;
+                    chk_pos = start;
+                    chk_cnt = 0;
+                    chk_dead = false;
                     // Symbol number n of my region lives in byte n & 3 of word n >> 2.  Only whole
                     // words are stored: up to three pending symbols wait in the top bytes of
                     // `acc` (earliest lowest), so a group of four always leaves as one 32-bit
@@ -831,6 +841,11 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                                 continue;
                             }
                             // the sub-block ends among them: the first is mine, the others may be
+                            // (where this last group begins is remembered: should the block end
+                            // in it, the search for its exact end bit starts here)
+                            chk_pos = pos;
+                            chk_cnt = (uint32_t)((wp - reg_s) / (uint32_t)kRegRow) * 4u + npend;
+                            chk_dead = last_dead != kNone;
                             put(four & 0xffu);
                             pos += e0 & 0xfu;
                             if (pos < my_hi) {
@@ -956,8 +971,27 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                 // the block ends inside my sub-block: find the bit behind its last code word
                 // (a dead step ends the search: the block goes to the general lane anyway, and
                 // the symbol count of a dead walk does not bound where this one would stop)
-                uint32_t p = start, dead = 0;
-                for (uint32_t q = 0; q < ncopy && !dead;) {
+                // The search starts at the last look-up group of my walk when the block ends in
+                // it (the usual case: the block ends where the next header was found), else at
+                // my first code word; whole groups of four are taken with the table loop.
+                uint32_t p = start, q = 0, dead = 0;
+                if (chk_cnt <= ncopy) {
+                    p = chk_pos;
+                    q = chk_cnt;
+                    dead = chk_dead ? 1u : 0u;
+                }
+                while (q < ncopy && !dead) {
+                    if (q + 4 <= ncopy) {
+                        BitWin b;
+                        win_load(b, sw_s, p);
+                        uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
+                        const uint32_t np = fast_look4(b, lut_s, p, e0, e1, e2, e3, h0, h1, h2, h3);
+                        if (!(((e0 | e1 | e2 | e3) & kFastFlags) | ((h0 | h1 | h2 | h3) >> 31))) {
+                            p = np;
+                            q += 4;
+                            continue;
+                        }
+                    }
                     const uint64_t r = fast_step(sw_s, lut_s, &ft, sm.nlong, p);
                     p = (uint32_t)r;
                     if (r & kStepOk) q++; else dead = 1;
@@ -974,13 +1008,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             }
             const bool fin_found = sm.fin_found != 0;
             const uint32_t total_copy = (uint64_t)total < remaining ? total : (uint32_t)remaining;
-            if (!fin_found) {
-                // the block goes on: request the next chunk's payload (same length as this one's)
-                pre_base = ((8ull * base16 + sm.sub_end[nact - 1]) >> 3) & ~uint64_t(15);
-                pre_n16 = min(cur_n16 + 2u, (uint32_t)(kFastStage / 16));  // (its start skew may differ)
-                stage_issue(pre_base, pre_n16);
-                pre_ok = true;
-            }
+            HUF_PROF(10);
 
             // (4) compaction into the (now free) stage buffer, coalesced copy-out
             if (can_write && total_copy) {
@@ -993,6 +1021,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     const uint32_t we = wb + kFastOutWin;
                     const uint32_t c0 = max(y0, wb), c1 = min(y1, we);
                     if (c0 < c1) region_copy(obuf + (c0 - wb), regw, c0 - y0, c1 - c0);
+                    HUF_PROF(11);
                     cta_sync();
                     HUF_PROF(5);
                     const uint32_t vend = min(yend, we) - wb;          // valid bytes end (window relative)
@@ -1023,8 +1052,10 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             }
             next_bit = 8ull * base16 + sm.sub_end[nact - 1];
             cta_sync();
+            stage_request((next_bit >> 3) & ~uint64_t(15));
         }
 
+        if (tma_pending) stage_wait();  // (left early: the stage buffer must be quiet for the next block)
         if (status == kOk && end_bit > room_end) status = kRedo;  // last code word leaves the readable bytes
         if (tid == 0) {
             a.blk_status[j] = status;
@@ -1034,7 +1065,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
     }
 #ifdef HUF_PHASE_PROF
     if (tid == 0) {
-        for (int k = 0; k < 10; k++) atomicAdd(&g_fast_prof[k], pacc[k]);
+        for (int k = 0; k < 12; k++) atomicAdd(&g_fast_prof[k], pacc[k]);
     }
 #endif
 }

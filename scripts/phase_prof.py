@@ -46,10 +46,12 @@ for rep in range(2):
     dec.decode_async(comp.data_ptr(), c, c, back.data_ptr(), n + 64, 0); r = dec.decode_finish()
 raw.huf_b200_debug_phase(out, 0)
 v = list(out)
-names = ["0 handout+table", "1 chunk head+stage", "2 thread0 walk", "3 wait+verify rounds", "4 scan+fin", "5 region copy", "6 copy-out"]
-tot = sum(v[:7])
+names = ["0 handout+table", "1 chunk head+stage", "2 thread0 walk", "3 wait+verify rounds", "4 scan+fin", "5 barrier behind region copy", "6 copy-out", None, None, None, "10 next-chunk request", "11 region copy (thread 0)"]
+tot = sum(v[:7]) + v[10] + v[11]
 print(shape, mib, "MiB ok", bool(torch.equal(back[:n], x)), [t for t in dec.kernel_times() if t[0] == "k_decode"])
 for k, nm in enumerate(names):
+    if nm is None:
+        continue
     print(f"  {nm:24s} {100.0 * v[k] / tot:6.2f} %   {v[k] / max(v[7], 1):9.0f} cycles per chunk")
 print(f"  chunks {v[7]}  blocks {v[9]}  repair rounds {v[8]}  chunks/block {v[7] / max(v[9], 1):.2f}  rounds/chunk {v[8] / max(v[7], 1):.3f}")
 print(f"  cycles per chunk (thread 0 timeline) {tot / max(v[7], 1):.0f}")
