@@ -27,18 +27,43 @@ struct PackFastSmem {
     __align__(16) uint32_t stage[kEncWarps][kPackStageWords];
 };
 
-__device__ __forceinline__ void acc_put_or(BitAcc &s, uint32_t *stage, uint32_t t, uint32_t l)
+// Append the l bits of t (left aligned) to a lane's bit accumulator: `hi` is the word under
+// construction with nb bits in it, the part of t that does not fit waits in `lo` (zero between
+// calls), and a full word is OR-ed into the staging window at shared address `at`.  The flush
+// is predicated, not branched: the kernel is issue bound and lanes flush at unrelated times.
+struct PackAcc {
+    uint32_t hi, lo, nb;
+    saddr_t at;
+};
+
+__device__ __forceinline__ void acc_put_or(PackAcc &s, uint32_t t, uint32_t l)
 {
     s.hi |= t >> s.nb;
-    s.lo |= __funnelshift_r(0u, t, s.nb);
+    s.lo = __funnelshift_r(0u, t, s.nb);
     s.nb += l;
+#ifdef HUF_EMU
     if (s.nb >= 32) {
-        atomicOr(&stage[s.widx], s.hi);
+        atomicOr(reinterpret_cast<uint32_t *>(s.at), s.hi);
         s.hi = s.lo;
         s.lo = 0;
         s.nb -= 32;
-        s.widx++;
+        s.at += 4;
     }
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ge.u32 p, %2, 32;\n\t"
+        "@p red.shared.or.b32 [%3], %0;\n\t"
+        "@p mov.u32 %0, %1;\n\t"
+        "@p mov.u32 %1, 0;\n\t"
+        "@p sub.u32 %2, %2, 32;\n\t"
+        "@p add.u32 %3, %3, 4;\n\t"
+        "}"
+        : "+r"(s.hi), "+r"(s.lo), "+r"(s.nb), "+r"(s.at)
+        :
+        : "memory");
+#endif
 }
 
 __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
@@ -96,6 +121,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         for (int i = lane; i < 256; i += 32) tab[i] = src[i];
     }
     uint32_t *stage = sm.stage[w];
+    const saddr_t stage_s = smem_addr(stage);
     for (int i = lane; i < kPackStageWords / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 
@@ -170,13 +196,13 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         const uint32_t incl = warp_incl_scan(total_l);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         const uint32_t start = q + incl - total_l;
-        BitAcc acc;
+        PackAcc acc;
         acc.hi = acc.lo = 0;
         acc.nb = start & 31;
-        acc.widx = start >> 5;
+        acc.at = stage_s + ((start >> 5) << 2);
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc_put_or(acc, stage, t[j], lp[j]);
-        if (acc.nb) atomicOr(&stage[acc.widx], acc.hi);
+        for (int j = 0; j < 8; j++) acc_put_or(acc, t[j], lp[j]);
+        if (acc.nb) atomicOr(stage + ((acc.at - stage_s) >> 2), acc.hi);
         __syncwarp();
 
         // ---- finished 16-byte lines leave coalesced; the unfinished line stays in front
