@@ -39,6 +39,8 @@
 //                  partial-output behaviour stay those of the general lane.
 #pragma once
 
+#include <type_traits>
+
 #include "dec_kernels.cuh"
 
 namespace hufb200 {
@@ -747,9 +749,11 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             const uint32_t my_lo = tid == 0 ? rel_start : min(A + (uint32_t)tid * sub, cover);
             const uint32_t my_hi = min(A + (uint32_t)(tid + 1) * sub, cover);
             uint32_t pos = my_lo, cnt = 0, last_dead = kNone;
-            // blind walk (every entry advances by its length field, specials and walks on a
-            // set root bit by one bit) from `from` to the first position >= limit
-            auto blind_to = [&](uint32_t from, uint32_t limit) -> uint32_t {
+            // blind walk (every entry advances by its length field, dead entries and walks on a
+            // set root bit by one bit, long code words by their exact length) from `from` to the
+            // first position >= limit
+            auto blind_walk = [&](auto long_tag, uint32_t from, uint32_t limit) -> uint32_t {
+                constexpr bool HAS_LONG = decltype(long_tag)::value;  // the block has long-code records
                 uint32_t p = from;
                 if (p >= limit) return p;
                 BitWin b;
@@ -769,6 +773,15 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     const uint32_t h3 = __funnelshift_l(lo, h2, l2);
                     const uint32_t l3 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h3))), h3);
                     const uint32_t np = p + ((l0 + l1 + l2 + l3) & 0x3fu);
+                    if (HAS_LONG && ((l0 | l1 | l2 | l3) & 0x80u)) {
+                        // a code word longer than the table reach among the four: this group is
+                        // walked with exact steps (a blind single-bit step would leave the
+                        // trajectory of the exact walk and cost a repair round later)
+                        for (int k = 0; k < 4 && p < limit; k++) p = (uint32_t)fast_step(sw_s, lut_s, &ft, sm.nlong, p);
+                        if (p >= limit) return p;
+                        win_load(b, sw_s, p);
+                        continue;
+                    }
                     if (np < limit) {  // four steps at a time while the fifth starts in front of the limit
                         win_advance(b, sw_s, p, np);
                         p = np;
@@ -780,6 +793,10 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     if (p < limit) p += l3 & 0x1fu;
                     return p;
                 }
+            };
+            // (blocks without long code words -- nearly all -- run the loop without that test)
+            auto blind_to = [&](uint32_t from, uint32_t limit) -> uint32_t {
+                return sm.nlong ? blind_walk(std::true_type{}, from, limit) : blind_walk(std::false_type{}, from, limit);
             };
             // start `warm` bits early (or at the proven chunk start when that is closer)
             const uint32_t warm_from = my_lo > rel_start + warm ? my_lo - warm : rel_start;
