@@ -144,9 +144,10 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
         uint32_t *slot = a.terms + j * kTermStride;
         // Ancestors whose right slot is still open, one bit per depth: every node opens its
         // right slot exactly once, so the pending stack is a bit mask and a pop is a clz.
-        uint64_t pend = 1;            // the root, depth 0
+        // (Eligible trees are at most kLongBits = 32 deep, so mask and path fit 32 bits.)
+        uint32_t pend = 1;            // the root, depth 0
         uint32_t i = 1, D = 1;        // slot being filled: depth D ...
-        uint64_t C = 0;               // ... reached by the path bits C
+        uint32_t C = 0;               // ... reached by the path bits C
         uint32_t nterm = 0, min_len = kTreeReach + 1;
         uint32_t wb = 0;              // first element of my staged window
         bool first = true;
@@ -204,66 +205,54 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
                         break;
                     }
                     elems3(i, e, e1, e2);
-                    // the right slot of the root must stay empty (table sits behind the root bit)
-                    if (D == 1 && C == 1 && e != -1) {
+                    // One straight-line body for the three kinds of slot content (leaf: v, absent,
+                    // absent / inner node / absent child): the lanes of a warp sit on different
+                    // kinds all the time, so the kinds are selected, not branched on; only the
+                    // exits (error, tree complete, window slide) leave the loop.
+                    const bool is_abs = e == -1;
+                    const bool is_leaf = !is_abs && e1 == -1 && e2 == -1;
+                    const bool is_inner = !is_abs && !is_leaf;
+                    // the right slot of the root must stay empty (table sits behind the root bit);
+                    // leaves below an inner node at depth 32 would need more than 32 bits
+                    if ((D == 1 && C == 1 && !is_abs) || (is_inner && D >= (uint32_t)kLongBits)) {
                         ok = false;
                         break;
                     }
-                    bool pop;
-                    if (e != -1) {
-                        if (e1 == -1 && e2 == -1) {  // leaf: v, absent, absent
-                            if (D <= (uint32_t)kTreeReach) {
-                                if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                                slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) |
-                                                ((uint32_t)(e & 0xff) << 8) | D;
-                                min_len = min(min_len, D);
-                            } else {
-                                if (nlong >= (uint32_t)kLongMax || nterm + 2 * nlong + 3 > (uint32_t)kTermStride) {
-                                    ok = false;
-                                    break;
-                                }
-                                slot[kTermStride - 2 * (nlong + 1)] = (uint32_t)(C << (kLongBits - D));
-                                slot[kTermStride - 2 * (nlong + 1) + 1] = (D << 8) | (uint32_t)(e & 0xff);
-                                nlong++;
-                            }
-                            i += 3;
-                            pop = true;
-                        } else {
-                            if (D >= (uint32_t)kLongBits) {  // leaves below would need more than 32 bits
-                                ok = false;
-                                break;
-                            }
-                            if (D == (uint32_t)kTreeReach) {  // inner node at the table depth: long codes
-                                if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                                slot[nterm++] = ((uint32_t)C << 16) | kFastLong;
-                            }
-                            pend |= 1ull << D;
-                            i++;
-                            D++;
-                            C <<= 1;
-                            pop = false;
-                        }
-                    } else {
-                        // consuming bit D walks into an absent child; below the table such a walk
-                        // simply matches no long-code record
-                        if (D <= (uint32_t)kTreeReach) {
-                            if (nterm + 2 * nlong + 2 > (uint32_t)kTermStride) { ok = false; break; }
-                            slot[nterm++] = ((uint32_t)(C << (kTreeReach - D)) << 16) | kFastDead;
-                        }
-                        i++;
-                        pop = true;
+                    const bool in_reach = D <= (uint32_t)kTreeReach;
+                    // table terminals: leaves and absent children inside the reach, inner nodes
+                    // exactly at the table depth (long codes); leaves below become records
+                    const bool emit_term = in_reach && (!is_inner || D == (uint32_t)kTreeReach);
+                    const bool emit_long = is_leaf && !in_reach;
+                    const uint32_t used = nterm + 2 * nlong;
+                    if ((emit_term && used + 2 > (uint32_t)kTermStride) ||
+                        (emit_long && (nlong >= (uint32_t)kLongMax || used + 3 > (uint32_t)kTermStride))) {
+                        ok = false;
+                        break;
                     }
-                    if (pop) {
-                        if (pend == 0) {  // every slot filled: the tree is complete
-                            meta = kMetaFast | (min_len << 8) | (nterm << 16);
-                            ok = false;
-                            break;
-                        }
-                        const uint32_t d = 63u - (uint32_t)__clzll((long long)pend);  // deepest open right slot
-                        pend &= ~(1ull << d);
-                        C = ((C >> (D - d)) << 1) | 1u;
-                        D = d + 1;
+                    const uint32_t sym = (uint32_t)(e & 0xff);
+                    if (emit_term) {
+                        const uint32_t entry = is_leaf ? ((sym << 8) | D) : (is_abs ? kFastDead : kFastLong);
+                        slot[nterm++] = ((C << ((uint32_t)kTreeReach - D)) << 16) | entry;
+                        if (is_leaf) min_len = min(min_len, D);
                     }
+                    if (emit_long) {
+                        slot[kTermStride - 2 * (nlong + 1)] = C << ((uint32_t)kLongBits - D);
+                        slot[kTermStride - 2 * (nlong + 1) + 1] = (D << 8) | sym;
+                        nlong++;
+                    }
+                    i += is_leaf ? 3u : 1u;
+                    if (!is_inner && pend == 0) {  // every slot filled: the tree is complete
+                        meta = kMetaFast | (min_len << 8) | (nterm << 16);
+                        ok = false;
+                        break;
+                    }
+                    // inner node: its right slot opens, go down to the left; otherwise continue
+                    // in the deepest open right slot (pend != 0 here)
+                    const uint32_t d = 31u - (uint32_t)__clz((int)pend);
+                    const uint32_t c_pop = ((uint32_t)((uint64_t)C >> (D - d)) << 1) | 1u;
+                    pend = is_inner ? (pend | (1u << D)) : (pend & ~(1u << d));
+                    C = is_inner ? (C << 1) : c_pop;
+                    D = is_inner ? D + 1 : d + 1;
                 }
                 if (!ok) active = false;
             }
