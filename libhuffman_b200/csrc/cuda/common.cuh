@@ -296,4 +296,41 @@ __device__ __forceinline__ uint64_t range_excl_scan(const T *in, uint64_t *out, 
     return run;
 }
 
+// Exclusive scan of in[0..n) by one CTA of kScanThreads threads with COALESCED accesses:
+// out[i] = base + sum(in[0..i)), returns base + sum(in[0..n)) (valid in every thread).
+// Every warp owns a contiguous run of elements and walks it in tiles of 32 (one element per
+// lane).  (A contiguous range per THREAD makes every load and store of a warp touch 32
+// different lines, and a single SM takes one line per cycle: 25 us for 16 K elements.)
+template <typename T>
+__device__ __forceinline__ uint64_t cta_excl_scan(const T *in, uint64_t *out, uint64_t n, uint64_t base,
+                                                  uint64_t *warp_tot /* shared, kScanThreads / 32 + 1 */)
+{
+    constexpr int kW = kScanThreads / 32;
+    const int w = warp_in_cta(), l = lane_id();
+    const uint64_t span = ((n + (uint64_t)kW * 32 - 1) / ((uint64_t)kW * 32)) * 32;  // per warp, tiles of 32
+    const uint64_t lo = n < (uint64_t)w * span ? n : (uint64_t)w * span;
+    const uint64_t hi = n < lo + span ? n : lo + span;
+    uint64_t s = 0;
+    for (uint64_t i = lo + l; i < hi; i += 32) s += in[i];
+    s = warp_sum(s);
+    if (l == 0) warp_tot[w] = s;
+    __syncthreads();
+    if (w == 0) {
+        const uint64_t t = warp_tot[l];
+        const uint64_t ti = warp_incl_scan(t);
+        warp_tot[l] = ti - t;
+        if (l == 31) warp_tot[kW] = ti;
+    }
+    __syncthreads();
+    uint64_t run = base + warp_tot[w];
+    for (uint64_t t0 = lo; t0 < hi; t0 += 32) {
+        const uint64_t i = t0 + l;
+        const uint64_t v = i < hi ? (uint64_t)in[i] : 0;
+        const uint64_t incl = warp_incl_scan(v);
+        if (i < hi) out[i] = run + incl - v;
+        run += __shfl_sync(kFull, incl, 31);
+    }
+    return base + warp_tot[kW];
+}
+
 }  // namespace hufb200

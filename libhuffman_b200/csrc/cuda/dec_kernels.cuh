@@ -269,23 +269,10 @@ __global__ void k_hint(DecArgs a, const uint64_t *__restrict__ hint, uint64_t n)
 // chunk counts -> exclusive offsets, total candidate count -> result[0].  One CTA.
 __global__ void __launch_bounds__(kScanThreads) k_scan_chunks(DecArgs a)
 {
-    __shared__ uint64_t warp_tot[kScanThreads / 32];
+    __shared__ uint64_t warp_tot[kScanThreads / 32 + 1];
     const uint64_t n = a.nchunks;
-    const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
-    const uint64_t lo = min(n, per * threadIdx.x);
-    const uint64_t hi = min(n, lo + per);
-    const uint64_t sum = range_sum(a.chunk_cnt, lo, hi);
-    const uint64_t incl = warp_incl_scan(sum);
-    if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
-    __syncthreads();
-    if (warp_in_cta() == 0) {
-        uint64_t t = warp_tot[lane_id()];
-        uint64_t ti = warp_incl_scan(t);
-        warp_tot[lane_id()] = ti - t;
-    }
-    __syncthreads();
-    const uint64_t run = range_excl_scan(a.chunk_cnt, a.chunk_off, lo, hi, warp_tot[warp_in_cta()] + incl - sum);
-    if (hi == n && lo < n) {
+    const uint64_t run = cta_excl_scan(a.chunk_cnt, a.chunk_off, n, 0, warp_tot);
+    if (threadIdx.x == 0) {
         a.chunk_off[n] = run;
         a.result[0] = run < a.max_cand ? run : a.max_cand;
         a.result[6] = run;  // > max_cand: workspace too small, the host re-sizes and reruns
@@ -296,6 +283,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_chunks(DecArgs a)
 __global__ void k_gather(DecArgs a)
 {
     const uint64_t n = a.result[0];
+    // the two maxima are reduced per warp before they touch the shared counters (one atomic
+    // per candidate on the same address serialises in L2: 25 us for 16 K candidates)
+    unsigned long long max_ol = 0, max_ext = 0;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
          j += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t off = a.cand[j];
@@ -305,36 +295,31 @@ __global__ void k_gather(DecArgs a)
         const uint64_t room = a.avail > off ? a.avail - off : 0;
         if (ol > 8ull * room) ol = 0;
         a.olen[j] = ol;
-        if (ol) atomicMax(reinterpret_cast<unsigned long long *>(&a.result[7]), (unsigned long long)ol);
+        if (ol > max_ol) max_ol = ol;
         // extent of this block's header + payload as the candidate list sees it: sizes the
         // shared-memory payload staging of k_decode on the next call
         const uint64_t next = j + 1 < n ? a.cand[j + 1] : a.avail;
-        if (next > off)
-            atomicMax(reinterpret_cast<unsigned long long *>(&a.result[9]), (unsigned long long)(next - off));
+        if (next > off && next - off > max_ext) max_ext = next - off;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(kFull, max_ol, d), o2 = __shfl_xor_sync(kFull, max_ext, d);
+        if (o1 > max_ol) max_ol = o1;
+        if (o2 > max_ext) max_ext = o2;
+    }
+    if (lane_id() == 0) {
+        if (max_ol) atomicMax(reinterpret_cast<unsigned long long *>(&a.result[7]), max_ol);
+        if (max_ext) atomicMax(reinterpret_cast<unsigned long long *>(&a.result[9]), max_ext);
     }
 }
 
 // exclusive scan of olen[0..ncand) -> out_off, with ncand read from device memory.
 __global__ void __launch_bounds__(kScanThreads) k_scan_olen(DecArgs a)
 {
-    __shared__ uint64_t warp_tot[kScanThreads / 32];
+    __shared__ uint64_t warp_tot[kScanThreads / 32 + 1];
     const uint64_t n = a.result[0];
-    const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
-    const uint64_t lo = min(n, per * threadIdx.x);
-    const uint64_t hi = min(n, lo + per);
-    const uint64_t sum = range_sum(a.olen, lo, hi);
-    const uint64_t incl = warp_incl_scan(sum);
-    if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
-    __syncthreads();
-    if (warp_in_cta() == 0) {
-        uint64_t t = warp_tot[lane_id()];
-        uint64_t ti = warp_incl_scan(t);
-        warp_tot[lane_id()] = ti - t;
-    }
-    __syncthreads();
-    const uint64_t run = range_excl_scan(a.olen, a.out_off, lo, hi, a.out_base + warp_tot[warp_in_cta()] + incl - sum);
-    if (hi == n && lo < n) a.out_off[n] = run;
-    if (n == 0 && threadIdx.x == 0) a.out_off[0] = a.out_base;
+    const uint64_t run = cta_excl_scan(a.olen, a.out_off, n, a.out_base, warp_tot);
+    if (threadIdx.x == 0) a.out_off[n] = run;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -430,29 +430,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_sizes(const uint64_t *__r
                                                              uint64_t n, uint64_t cap,
                                                              uint32_t *status)
 {
-    __shared__ uint64_t warp_tot[kScanThreads / 32];
-    const uint64_t per = (n + kScanThreads - 1) / kScanThreads;
-    const uint64_t lo = min(n, per * threadIdx.x);
-    const uint64_t hi = min(n, lo + per);
-
-    const uint64_t sum = range_sum(in, lo, hi);
-
-    const uint64_t incl = warp_incl_scan(sum);
-    if (lane_id() == 31) warp_tot[warp_in_cta()] = incl;
-    __syncthreads();
-    if (warp_in_cta() == 0) {
-        uint64_t t = warp_tot[lane_id()];
-        uint64_t ti = warp_incl_scan(t);
-        warp_tot[lane_id()] = ti - t;  // exclusive
-    }
-    __syncthreads();
+    __shared__ uint64_t warp_tot[kScanThreads / 32 + 1];
     // out[0] holds the running total of the previous passes (0 for the first pass)
     const uint64_t base = out[0];
     __syncthreads();
-    const uint64_t run = range_excl_scan(in, out, lo, hi, base + warp_tot[warp_in_cta()] + incl - sum);
-    if (hi == n && lo < n) {
-        out[n] = run;
-        if (run > cap) atomicMax(&status[0], (uint32_t)kErrNoMem);
+    const uint64_t total = cta_excl_scan(in, out, n, base, warp_tot);
+    if (threadIdx.x == 0) {
+        out[n] = total;
+        if (total > cap) atomicMax(&status[0], (uint32_t)kErrNoMem);
     }
 }
 
