@@ -981,12 +981,30 @@ __global__ void __launch_bounds__(kScanThreads) k_verify(DecArgs a)
     const uint64_t n = a.result[0];
     if (threadIdx.x == 0) first_bad = n;
     __syncthreads();
-    for (uint64_t j = threadIdx.x; j < n; j += kScanThreads) {
-        bool bad = a.blk_status[j] != kOk;
-        if (!bad && j + 1 < n && a.end_off[j] != a.cand[j + 1]) bad = true;
-        // a block whose output does not fit is not proven either
-        if (!bad && !a.count_only && a.out_off[j] + a.olen[j] > a.out_cap) bad = true;
-        if (bad) atomicMin(&first_bad, (unsigned long long)j);
+    // (four candidates per thread and round, all their loads in flight together: the kernel is
+    // one CTA and a chain of dependent memory round trips otherwise)
+    for (uint64_t j0 = threadIdx.x; j0 < n; j0 += 4 * kScanThreads) {
+        uint32_t st[4];
+        uint64_t eo[4], nx[4], oo[4], ol[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t j = j0 + (uint64_t)q * kScanThreads;
+            const bool in = j < n;
+            st[q] = in ? a.blk_status[j] : (uint32_t)kOk;
+            eo[q] = in ? a.end_off[j] : 0;
+            nx[q] = in && j + 1 < n ? a.cand[j + 1] : eo[q];
+            oo[q] = in ? a.out_off[j] : 0;
+            ol[q] = in ? a.olen[j] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t j = j0 + (uint64_t)q * kScanThreads;
+            bool bad = st[q] != kOk;
+            if (!bad && j + 1 < n && eo[q] != nx[q]) bad = true;
+            // a block whose output does not fit is not proven either
+            if (!bad && !a.count_only && oo[q] + ol[q] > a.out_cap) bad = true;
+            if (j < n && bad) atomicMin(&first_bad, (unsigned long long)j);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
