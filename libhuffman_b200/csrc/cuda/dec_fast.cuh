@@ -959,15 +959,15 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
             if ((tid & 31) == 31) sm.warp_tot[tid >> 5] = incl;
             if (tid == 0) sm.fin_found = 0;
             cta_sync();
-            if (tid < 32) {
-                const uint32_t t = tid < kFT / 32 ? sm.warp_tot[tid] : 0;
-                const uint32_t ti = warp_incl_scan(t);
-                if (tid < kFT / 32) sm.warp_tot[tid] = ti - t;
-                if (tid == kFT / 32 - 1) sm.total = ti;
+            // (a handful of warp totals: every thread adds up the ones in front of its warp
+            // itself, which saves a second barrier round)
+            uint32_t before = incl - cnt, total = 0;
+#pragma unroll
+            for (int wq = 0; wq < kFT / 32; wq++) {
+                const uint32_t t = sm.warp_tot[wq];
+                if (wq < (tid >> 5)) before += t;
+                total += t;
             }
-            cta_sync();
-            const uint32_t before = sm.warp_tot[tid >> 5] + incl - cnt;
-            const uint32_t total = sm.total;
             const uint64_t remaining = orig_len - produced;
             const bool in_blk = (uint64_t)before < remaining && cnt > 0;
             const bool fin = in_blk && (uint64_t)before + cnt >= remaining;
