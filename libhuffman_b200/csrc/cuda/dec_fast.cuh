@@ -968,6 +968,9 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                 if (wq < (tid >> 5)) before += t;
                 total += t;
             }
+            const uint32_t last_end = sm.sub_end[nact - 1];  // (final since the verification; read
+                                                             // here, behind a barrier, so that the
+                                                             // chunk needs none at its end)
             const uint64_t remaining = orig_len - produced;
             const bool in_blk = (uint64_t)before < remaining && cnt > 0;
             const bool fin = in_blk && (uint64_t)before + cnt >= remaining;
@@ -1056,8 +1059,10 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                 end_bit = 8ull * base16 + sm.fin_end;
                 break;
             }
-            next_bit = 8ull * base16 + sm.sub_end[nact - 1];
-            cta_sync();
+            next_bit = 8ull * base16 + last_end;
+            // (the copy-out ended with a barrier: nobody reads the stage buffer any more; a
+            // chunk that wrote nothing has not passed one since the region copies)
+            if (!(can_write && total_copy)) cta_sync();
             stage_request((next_bit >> 3) & ~uint64_t(15));
         }
 
