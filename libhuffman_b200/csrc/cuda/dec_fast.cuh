@@ -76,17 +76,17 @@ constexpr int kRegCap = 4 * kRegWords;    // symbols a region can hold
 constexpr int kRegRow = kFT * 4;          // regions are interleaved: word c of thread t sits at
                                           // row c, column t -- the bank is the thread's, so region
                                           // stores and loads never conflict whatever c each lane is at
-constexpr int kMaxSubWords = 27;          // payload words per thread per chunk (odd)
+constexpr int kMaxSubWords = 29;          // payload words per thread per chunk (odd)
 constexpr int kFastStage = kFT * kMaxSubWords * 4 + 64;  // staged payload bytes (+ start skew, slack)
 constexpr int kFastOutWin = kFT * kMaxSubWords * 4;      // compaction window (multiple of 16)
 // Dynamic shared memory of k_decode (the kernel has no static shared memory, so the block
 // starts at shared-window address 0x400 behind the 1 KB the system reserves):
 //   [0, kFastStage)            staged payload / compaction window
-//   [kFastStage, kFastLutOff)  FastSmall: per-thread hand-over words and CTA scalars
 //   [kFastLutOff, +8 KB)       lookup table, at window address 0x4000: 8 KB aligned, so the
 //                              table index is OR-ed into the base
 //   [kFastRegOff, ...)         symbol regions, one per thread
-//   [kFastTailOff, kFastDyn)   FastTail: long-code records, re-speculation classes
+//   [kFastTailOff, ...)        FastTail: long-code records, re-speculation classes
+//   [kFastSmallOff, kFastDyn)  FastSmall: per-thread hand-over words and CTA scalars
 // kFastDyn + 1 KB stays below a quarter of the 228 KB an SM offers: four CTAs per SM.
 constexpr int kFastLutOff = 15360;
 constexpr int kFastLutAlign = 2 * kLutSize;               // 8 KB
@@ -289,8 +289,11 @@ struct FastTail {
     uint16_t long_ent[kLongMax];   // length << 8 | symbol
 };
 
-constexpr int kFastDyn = kFastTailOff + (int)sizeof(FastTail);
-static_assert(kFastStage + (int)sizeof(FastSmall) <= kFastLutOff, "FastSmall must fit in front of the table");
+constexpr int kFastSmallOff = kFastTailOff + (int)sizeof(FastTail);
+constexpr int kFastDyn = kFastSmallOff + (int)sizeof(FastSmall);
+static_assert(kFastStage <= kFastLutOff, "the stage must fit in front of the table");
+static_assert(kFastDyn + 1024 <= 233472 / 4, "four CTAs per SM");
+static_assert(sizeof(FastTail) % 8 == 0, "FastSmall holds 64-bit words");
 static_assert(kFastStage % 16 == 0 && kFastRegOff % 16 == 0 && kFastTailOff % 8 == 0, "alignment");
 
 // Byte offset of the table entry selected by the twelve bits BEHIND the root bit of the left
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
 #else
     extern __shared__ __align__(16) uint8_t dyn[];
 #endif
-    FastSmall &sm = *reinterpret_cast<FastSmall *>(dyn + kFastStage);
+    FastSmall &sm = *reinterpret_cast<FastSmall *>(dyn + kFastSmallOff);
     FastTail &ft = *reinterpret_cast<FastTail *>(dyn + kFastTailOff);
     const int tid = threadIdx.x;
 #ifdef HUF_PHASE_PROF
