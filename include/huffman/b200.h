@@ -107,6 +107,51 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *ctx, const void *d_in, uint64_t
                                  uint64_t length, uint64_t *out_len, uint64_t *nblocks,
                                  void *stream);
 
+/* Like huf_b200_decode_async, but the pass starts at byte offset `first` of d_in, which the
+ * caller has proven to be a block start (the end of the previous block); output begins at
+ * d_out[0].  This is how the host lane decodes a stream span by span. */
+huf_error_t huf_b200_decode_async_at(huf_b200_ctx_t *ctx, const void *d_in, uint64_t avail,
+                                     uint64_t length, uint64_t first, void *d_out,
+                                     uint64_t out_capacity, void *stream);
+
+/* ---- host-buffer lanes ----------------------------------------------------------------------
+ * What huf_encode / huf_decode run below their stream objects (reference src/io.c:9-226,
+ * src/bufio.c:149-287): the bytes come from a source and go to a sink in HOST memory, and the
+ * library overlaps source -> pinned -> HBM, the kernels, and HBM -> pinned -> sink over spans of
+ * whole blocks (three CUDA streams, a pool of copy threads).  A source is either contiguous
+ * memory (`data`/`size`, any host memory) or a pull callback that fills the pinned buffer it is
+ * handed; a sink either lends memory (`reserve` returns where the next `count` bytes go, `commit`
+ * accounts for them) or takes pushes. */
+typedef struct huf_b200_source {
+    const void *data;   /* contiguous readable bytes, or NULL: use pull */
+    uint64_t size;      /* bytes readable at data */
+    /* Fill dst with up to `want` of the next bytes; *got < want means end of data. */
+    huf_error_t (*pull)(void *arg, void *dst, uint64_t want, uint64_t *got);
+    void *arg;
+} huf_b200_source_t;
+
+typedef struct huf_b200_sink {
+    /* Make room for `count` more bytes and return where they go in *dst (NULL: use push). */
+    huf_error_t (*reserve)(void *arg, uint64_t count, void **dst);
+    huf_error_t (*commit)(void *arg, uint64_t count);
+    huf_error_t (*push)(void *arg, const void *src, uint64_t count);
+    void *arg;
+} huf_b200_sink_t;
+
+/* huf_encode below the streams: `length` bytes of `src` in blocks of `blocksize` (0 => one
+ * block).  A source that ends early gives HUF_ERROR_READ_WRITE after the complete blocks were
+ * delivered (src/encoder.c:296-299).  *consumed = source bytes taken. */
+huf_error_t huf_b200_encode_host(huf_b200_ctx_t *ctx, const huf_b200_source_t *src, uint64_t length,
+                                 uint64_t blocksize, const huf_b200_sink_t *dst, uint64_t *consumed);
+
+/* huf_decode below the streams: blocks are started while consumed < `length`
+ * (src/decoder.c:218); a contiguous source lends all of its bytes (the last block may reach
+ * past `length`), a pull source is asked for `length` bytes and for more only when a block
+ * needs them.  Output decoded before a failing block is still delivered.  *consumed =
+ * compressed bytes of the whole blocks decoded. */
+huf_error_t huf_b200_decode_host(huf_b200_ctx_t *ctx, const huf_b200_source_t *src, uint64_t length,
+                                 const huf_b200_sink_t *dst, uint64_t *consumed);
+
 /* Counters for benches/tests: kernels launched by the last *_async call. */
 uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx);
 /* After decode_finish: candidate blocks of the last pass that the fast decode lane declined

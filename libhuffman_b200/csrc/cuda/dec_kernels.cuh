@@ -1031,6 +1031,12 @@ __global__ void __launch_bounds__(kScanThreads) k_verify(DecArgs a)
             produced = a.out_off[n];
         }
         if (!done && reached >= a.length) done = 1;
+        if (!done && reached >= a.avail) {
+            // `length` asks for another block but the readable bytes end here: the reference
+            // fails on the read of the next header (src/decoder.c:220-229, bufio short read)
+            status = kErrIO;
+            done = 1;
+        }
         a.result[1] = proven;
         a.result[2] = status;
         a.result[3] = reached;

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -17,6 +19,7 @@
 #include "enc_kernels.cuh"
 #include "enc_build.cuh"
 #include "enc_pack.cuh"
+#include "host_pipe.cuh"
 
 using namespace hufb200;
 
@@ -119,6 +122,7 @@ struct huf_b200_ctx {
 
     // decode call in flight
     bool dec_pending = false;
+    uint64_t dec_first = 0;         // offset the pending decode call started at
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
     const uint64_t *hint_off = nullptr;  // optional block index for the next decode (device pointer)
@@ -128,6 +132,9 @@ struct huf_b200_ctx {
     bool fast_ready = false;        // k_decode attributes set
     int fast_per_sm = 1;
     uint64_t dec_stage_want = 80 * 1024;  // payload bytes of one block staged in shared memory
+
+    pipe::PipeState pipe;           // streams, events and cached buffers of the host-buffer lanes
+    uint64_t dec_margin = 1u << 20; // host lane: bytes kept back behind a pass so its last block is whole
 };
 
 namespace {
@@ -146,6 +153,12 @@ huf_error_t cuda_fail(cudaError_t e, int line = 0)
         if (e__ != cudaSuccess) return cuda_fail(e__, __LINE__); \
     } while (0)
 
+#define HUF_TRY_CXX(expr)                              \
+    do {                                               \
+        huf_error_t e__ = (expr);                      \
+        if (e__ != HUF_ERROR_SUCCESS) return e__;      \
+    } while (0)
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
@@ -159,6 +172,17 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// Timed launches of a call whose times were never read (huf_b200_kernel_times): release their
+// events before the slots are reused.
+void drop_timed(huf_b200_ctx *c)
+{
+    for (int i = 0; i < c->ntimed; i++) {
+        cudaEventDestroy(c->timed[i].t0);
+        cudaEventDestroy(c->timed[i].t1);
+    }
+    c->ntimed = 0;
+}
 
 cudaStream_t pick_stream(huf_b200_ctx *c, void *stream)
 {
@@ -183,7 +207,6 @@ struct StagePool {
     uint8_t *pin[2] = {nullptr, nullptr};
     cudaEvent_t done[2];
     cudaStream_t stream = nullptr;
-    unsigned threads = 1;
 };
 StagePool g_stage;
 
@@ -205,11 +228,6 @@ bool stage_ready()
         cudaGetLastError();
         return false;
     }
-    unsigned hc = std::thread::hardware_concurrency();
-    const char *env = getenv("HUF_B200_COPY_THREADS");
-    unsigned want = env ? (unsigned)atoi(env) : 8u;
-    if (hc && want > hc) want = hc;
-    g_stage.threads = want ? want : 1;
     g_stage.ok = true;
     return true;
 #endif
@@ -217,21 +235,7 @@ bool stage_ready()
 
 void parallel_memcpy(void *dst, const void *src, uint64_t bytes)
 {
-    const unsigned nt = g_stage.threads;
-    if (nt <= 1 || bytes < (4ull << 20)) {
-        memcpy(dst, src, bytes);
-        return;
-    }
-    const uint64_t slice = ((bytes + nt - 1) / nt + 4095) & ~uint64_t(4095);
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nt; t++) {
-        const uint64_t at = (uint64_t)t * slice;
-        if (at >= bytes) break;
-        const uint64_t len = bytes - at < slice ? bytes - at : slice;
-        pool.emplace_back([=] { memcpy(static_cast<uint8_t *>(dst) + at, static_cast<const uint8_t *>(src) + at, len); });
-    }
-    memcpy(dst, src, bytes < slice ? bytes : slice);
-    for (auto &th : pool) th.join();
+    pipe::CopyPool::get().copy(dst, src, bytes);
 }
 
 }  // namespace
@@ -288,6 +292,8 @@ huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx)
     if (c) {
         DeviceGuard g(c->device);
         cudaDeviceSynchronize();
+        drop_timed(c);
+        c->pipe.release();
         if (c->enc_ws.base) cudaFree(c->enc_ws.base);
         if (c->dec_ws.base) cudaFree(c->dec_ws.base);
         if (c->d_status) cudaFree(c->d_status);
@@ -358,23 +364,38 @@ huf_error_t huf_b200_kernel_times(huf_b200_ctx_t *c, char *buf, uint64_t buflen)
 // encode
 // ------------------------------------------------------------------------------------------
 
+namespace {
+huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length, uint64_t blocksize,
+                           void *d_out, uint64_t out_capacity, void *stream);
+}
+
 huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t length,
                                   uint64_t blocksize, void *d_out, uint64_t out_capacity,
                                   void *stream)
 {
     if (!c || (!d_in && length) || (!d_out && length)) return HUF_ERROR_INVALID_ARGUMENT;
-    if (c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->dec_pending || c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    // the call is pending (encode_finish owed) only once everything was enqueued: a failure on
+    // the way (workspace allocation, launch error) leaves the context free for the next call
+    const huf_error_t e = encode_enqueue(c, d_in, length, blocksize, d_out, out_capacity, stream);
+    c->enc_pending = e == HUF_ERROR_SUCCESS;
+    return e;
+}
+
+namespace {
+huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length, uint64_t blocksize,
+                           void *d_out, uint64_t out_capacity, void *stream)
+{
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
     cudaStream_t st = pick_stream(c, stream);
     c->cur = st;
     c->launches = 0;
-    c->ntimed = 0;
+    drop_timed(c);
     if (!blocksize) blocksize = length;
 
     const uint64_t nblocks = huf_b200_block_count(length, blocksize);
     c->enc_nblocks = nblocks;
-    c->enc_pending = true;
     EncArgs &a = c->enc;
     memset(&a, 0, sizeof(a));
     if (!nblocks) return HUF_ERROR_SUCCESS;
@@ -452,6 +473,7 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
                            cudaMemcpyDeviceToHost, st));
     return HUF_ERROR_SUCCESS;
 }
+}  // namespace
 
 huf_error_t huf_b200_encode_finish(huf_b200_ctx_t *c, uint64_t *out_len)
 {
@@ -594,19 +616,18 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
 
 }  // namespace
 
-huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
-                                  uint64_t length, void *d_out, uint64_t out_capacity,
-                                  void *stream)
+huf_error_t huf_b200_decode_async_at(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                     uint64_t length, uint64_t first, void *d_out,
+                                     uint64_t out_capacity, void *stream)
 {
     if (!c || (!d_in && avail) || (!d_out && out_capacity)) return HUF_ERROR_INVALID_ARGUMENT;
-    if (c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
     c->cur = pick_stream(c, stream);
     c->launches = 0;
-    c->ntimed = 0;
+    drop_timed(c);
     c->dec_dense = false;
-    c->dec_pending = true;
     DecArgs &a = c->dec;
     memset(&a, 0, sizeof(a));
     a.in = static_cast<const uint8_t *>(d_in);
@@ -614,8 +635,19 @@ huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
     a.length = length;
     a.out = static_cast<uint8_t *>(d_out);
     a.out_cap = out_capacity;
-    if (!length) return HUF_ERROR_SUCCESS;  // src/decoder.c:218: nothing to consume
-    return dec_enqueue(c, 0, 0, false, 0);
+    // (pending only after a successful enqueue, see huf_b200_encode_async)
+    const huf_error_t e = length > first ? dec_enqueue(c, first, 0, false, 0)
+                                         : HUF_ERROR_SUCCESS;  // src/decoder.c:218: nothing to consume
+    c->dec_first = first;
+    c->dec_pending = e == HUF_ERROR_SUCCESS;
+    return e;
+}
+
+huf_error_t huf_b200_decode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                  uint64_t length, void *d_out, uint64_t out_capacity,
+                                  void *stream)
+{
+    return huf_b200_decode_async_at(c, d_in, avail, length, 0, d_out, out_capacity, stream);
 }
 
 huf_error_t huf_b200_decode_hint_offsets(huf_b200_ctx_t *c, const uint64_t *d_offsets, uint64_t nblocks)
@@ -632,8 +664,8 @@ huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_
     if (!c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
     c->dec_pending = false;
     *out_len = 0;
-    if (consumed) *consumed = 0;
-    if (!c->dec.length) return HUF_ERROR_SUCCESS;
+    if (consumed) *consumed = c->dec_first;
+    if (c->dec.length <= c->dec_first) return HUF_ERROR_SUCCESS;
     DeviceGuard g(c->device);
 
     for (;;) {
@@ -658,7 +690,11 @@ huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_
         if (consumed) *consumed = r[3];
         if (r[5]) return (huf_error_t)r[2];
         // The speculative chain broke at a block boundary that no candidate marks (foreign
-        // header shape or a false positive): restart from the last proven position.
+        // header shape or a false positive): restart from the last proven position.  A pass
+        // always proves the block at its start or reports its error, so a pass that did not
+        // move cannot happen; should it ever, fail like a reader that runs dry instead of
+        // spinning with the caller's lock held.
+        if (r[3] <= c->dec.first) return HUF_ERROR_READ_WRITE;
         huf_error_t e = dec_enqueue(c, r[3], r[4], false, 0);
         if (e != HUF_ERROR_SUCCESS) return e;
     }
@@ -728,12 +764,7 @@ huf_error_t huf_b200_dev_free(void *d_ptr)
 // pipeline over pinned bounce buffers: the DMA of one chunk overlaps the host-side memcpy of
 // the next, and that memcpy is split over a few threads (a freshly allocated destination is
 // first-touched by all of them instead of page-faulting on one core).
-static double now_s()
-{
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec + 1e-9 * ts.tv_nsec;
-}
+using pipe::now_s;
 
 struct CopyTimer {
     const char *what;
@@ -805,6 +836,443 @@ huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
         parallel_memcpy(dst + at, g_stage.pin[c & 1], len);
     }
     return HUF_ERROR_SUCCESS;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// host-buffer lanes (see host_pipe.cuh)
+// ------------------------------------------------------------------------------------------
+
+huf_error_t huf_b200_encode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src, uint64_t length,
+                                 uint64_t blocksize, const huf_b200_sink_t *dst, uint64_t *consumed)
+{
+    using namespace pipe;
+    if (!c || !src || !dst) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (consumed) *consumed = 0;
+    if (!length) return HUF_ERROR_SUCCESS;
+    DeviceGuard g(c->device);
+    if (!g.ok) return HUF_ERROR_FATAL;
+    PipeState &ps = c->pipe;
+    HUF_TRY_CXX(ps.init());
+
+    const uint64_t bs = blocksize ? blocksize : length;
+    uint64_t span = span_bytes() / bs * bs;  // whole blocks per span; a larger block is its own span
+    if (!span) span = bs;
+    if (span > length) span = length;
+    const uint64_t nspans = (length + span - 1) / span;
+    const int nslots = nspans < (uint64_t)kSlots ? (int)nspans : kSlots;
+    const uint64_t out_cap = huf_b200_encode_bound(span, bs);
+    for (int i = 0; i < nslots; i++) {
+        HUF_TRY_CXX(reserve_pinned(ps.pin_in[i], span));
+        HUF_TRY_CXX(reserve_pinned(ps.pin_out[i], out_cap));
+        HUF_TRY_CXX(reserve_device(ps.d_in[i], span));
+        HUF_TRY_CXX(reserve_device(ps.d_out[i], out_cap));
+    }
+
+    struct Slot {
+        uint64_t in_len = 0, out_len = 0;
+        bool short_read = false;
+    };
+    Slot slots[kSlots];
+    Chan<int> free_q, in_q, out_q;
+    for (int i = 0; i < nslots; i++) free_q.push(i);
+    std::atomic<int> fail{HUF_ERROR_SUCCESS};   // first error of any stage
+    std::atomic<uint64_t> taken{0};
+    StageTimes tm;
+    const double t_start = now_s();
+    const int device = c->device;
+
+    auto set_fail = [&](huf_error_t e) {
+        int ok = HUF_ERROR_SUCCESS;
+        fail.compare_exchange_strong(ok, (int)e);
+    };
+
+    // ---- stage "in": source -> pinned -> HBM
+    auto stage_in = [&]() {
+        cudaSetDevice(device);
+        for (uint64_t k = 0; k < nspans; k++) {
+            const int i = free_q.pop();
+            if (fail.load() != HUF_ERROR_SUCCESS) {
+                free_q.push(i);
+                break;
+            }
+            Slot &sl = slots[i];
+            const uint64_t want = length - k * span < span ? length - k * span : span;
+            uint64_t got = 0;
+            const double t0 = now_s();
+            huf_error_t e = source_fill(*src, k * span, ps.pin_in[i].p, want, &got);
+            tm.fill += now_s() - t0;
+            if (e != HUF_ERROR_SUCCESS) {
+                set_fail(e);
+                free_q.push(i);
+                break;
+            }
+            taken.fetch_add(got);
+            sl.short_read = got < want;
+            sl.in_len = sl.short_read ? got / bs * bs : got;  // a short read ends after whole blocks
+            sl.out_len = 0;
+            if (sl.in_len) {
+                cudaMemcpyAsync(ps.d_in[i].p, ps.pin_in[i].p, sl.in_len, cudaMemcpyHostToDevice, ps.s_h2d);
+                cudaEventRecord(ps.ev_h2d[i], ps.s_h2d);
+            }
+            in_q.push(i);
+            if (sl.short_read) break;
+        }
+        in_q.push(kEnd);
+    };
+
+    // ---- stage "out": HBM -> pinned (issued by the kernel stage) -> sink
+    auto stage_out = [&]() {
+        cudaSetDevice(device);
+        for (;;) {
+            const int i = out_q.pop();
+            if (i == kEnd) break;
+            Slot &sl = slots[i];
+            if (sl.out_len && fail.load() == HUF_ERROR_SUCCESS) {
+                double t0 = now_s();
+                if (cudaEventSynchronize(ps.ev_d2h[i]) != cudaSuccess) {
+                    cudaGetLastError();
+                    set_fail(HUF_ERROR_FATAL);
+                } else {
+                    tm.d2h_wait += now_s() - t0;
+                    t0 = now_s();
+                    huf_error_t e = sink_deliver(*dst, ps.pin_out[i].p, sl.out_len);
+                    tm.deliver += now_s() - t0;
+                    if (e != HUF_ERROR_SUCCESS) set_fail(e);
+                }
+            }
+            free_q.push(i);
+        }
+    };
+
+    // ---- kernel stage (this thread)
+    auto stage_kernels = [&]() {
+        bool short_read = false;
+        for (;;) {
+            const int i = in_q.pop();
+            if (i == kEnd) break;
+            Slot &sl = slots[i];
+            if (sl.in_len && fail.load() == HUF_ERROR_SUCCESS) {
+                const double t0 = now_s();
+                cudaStreamWaitEvent(c->own_stream, ps.ev_h2d[i], 0);
+                // (the result also has to fit the pinned buffer it is copied to)
+                const uint64_t cap = ps.d_out[i].cap < ps.pin_out[i].cap ? ps.d_out[i].cap : ps.pin_out[i].cap;
+                huf_error_t e = huf_b200_encode_async(c, ps.d_in[i].p, sl.in_len, bs, ps.d_out[i].p, cap,
+                                                      HUF_B200_STREAM_PRIVATE);
+                uint64_t n = 0;
+                if (e == HUF_ERROR_SUCCESS) e = huf_b200_encode_finish(c, &n);
+                tm.kern += now_s() - t0;
+                if (e != HUF_ERROR_SUCCESS) {
+                    set_fail(e);
+                } else {
+                    sl.out_len = n;
+                    cudaMemcpyAsync(ps.pin_out[i].p, ps.d_out[i].p, n, cudaMemcpyDeviceToHost, ps.s_d2h);
+                    cudaEventRecord(ps.ev_d2h[i], ps.s_d2h);
+                }
+            }
+            short_read = short_read || sl.short_read;
+            out_q.push(i);
+        }
+        out_q.push(kEnd);
+        return short_read;
+    };
+
+    bool short_read;
+    if (nspans == 1) {
+        // one span: nothing to overlap, no threads
+        stage_in();
+        short_read = stage_kernels();
+        stage_out();
+    } else {
+        std::thread t_in(stage_in), t_out(stage_out);
+        short_read = stage_kernels();
+        t_in.join();
+        t_out.join();
+    }
+    cudaStreamSynchronize(ps.s_h2d);
+    cudaStreamSynchronize(ps.s_d2h);
+    if (consumed) *consumed = taken.load();
+    if (debug_on() && length >= (1u << 20)) {
+        const double dt = now_s() - t_start;
+        fprintf(stderr,
+                "huf_b200: encode_host %.1f MiB in %.1f ms (%.2f GB/s): %llu spans of %.1f MiB; busy ms: fill %.1f kernels+sync %.1f "
+                "d2h wait %.1f deliver %.1f\n",
+                length / 1048576.0, dt * 1e3, length / dt / 1e9, (unsigned long long)nspans, span / 1048576.0, tm.fill * 1e3,
+                tm.kern * 1e3, tm.d2h_wait * 1e3, tm.deliver * 1e3);
+    }
+    const huf_error_t e = (huf_error_t)fail.load();
+    if (e != HUF_ERROR_SUCCESS) return e;
+    return short_read ? HUF_ERROR_READ_WRITE : HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src, uint64_t length,
+                                 const huf_b200_sink_t *dst, uint64_t *consumed)
+{
+    using namespace pipe;
+    if (!c || !src || !dst) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (consumed) *consumed = 0;
+    if (!length) return HUF_ERROR_SUCCESS;
+    DeviceGuard g(c->device);
+    if (!g.ok) return HUF_ERROR_FATAL;
+    PipeState &ps = c->pipe;
+    HUF_TRY_CXX(ps.init());
+
+    const bool lent = src->data != nullptr;
+    // bytes the in-stage brings in on its own: everything a contiguous source has, `length` bytes
+    // of a pull source (more are pulled only when a block turns out to need them)
+    const uint64_t planned = lent ? src->size : length;
+    const uint64_t span = span_bytes();
+    const uint64_t nspans = planned ? (planned + span - 1) / span : 0;
+    HUF_TRY_CXX(reserve_device(ps.d_stream, planned + 64));
+    for (int i = 0; i < 2; i++) HUF_TRY_CXX(reserve_pinned(ps.pin_in[i], span < planned ? span : planned));
+    // output slots: a pass decodes about one span of input; the capacity adapts to the data
+    uint64_t out_cap = 2 * span;
+    for (int i = 0; i < kSlots; i++) {
+        HUF_TRY_CXX(reserve_device(ps.d_out[i], out_cap));
+        HUF_TRY_CXX(reserve_pinned(ps.pin_out[i], out_cap));
+    }
+
+    struct Slot {
+        uint64_t out_len = 0;
+    };
+    Slot slots[kSlots];
+    Chan<int> free_q, out_q;
+    for (int i = 0; i < kSlots; i++) free_q.push(i);
+    std::atomic<int> fail{HUF_ERROR_SUCCESS};
+    StageTimes tm;
+    const double t_start = now_s();
+    const int device = c->device;
+    auto set_fail = [&](huf_error_t e) {
+        int ok = HUF_ERROR_SUCCESS;
+        fail.compare_exchange_strong(ok, (int)e);
+    };
+
+    // resident = compressed bytes in HBM so far; in_done = the in-stage has brought in all it will
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t resident = 0;
+    bool in_done = false, in_eof = false, stop_in = false;
+
+    auto stage_in = [&]() {
+        cudaSetDevice(device);
+        uint64_t at = 0;
+        cudaEvent_t ev[2] = {ps.ev_h2d[0], ps.ev_h2d[1]};
+        uint64_t issued[2] = {0, 0};
+        bool eof = false;
+        for (uint64_t k = 0; k < nspans && !eof; k++) {
+            const int b = (int)(k & 1);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (stop_in) break;
+            }
+            if (k >= 2) {
+                // the copy that last used this pinned buffer is done: publish its bytes
+                cudaEventSynchronize(ev[b]);
+                std::lock_guard<std::mutex> lk(mu);
+                resident = issued[b];
+                cv.notify_all();
+            }
+            const uint64_t want = planned - at < span ? planned - at : span;
+            uint64_t got = 0;
+            const double t0 = now_s();
+            huf_error_t e = source_fill(*src, at, ps.pin_in[b].p, want, &got);
+            tm.fill += now_s() - t0;
+            if (e != HUF_ERROR_SUCCESS) {
+                set_fail(e);
+                break;
+            }
+            if (got) {
+                cudaMemcpyAsync(ps.d_stream.p + at, ps.pin_in[b].p, got, cudaMemcpyHostToDevice, ps.s_h2d);
+                cudaEventRecord(ev[b], ps.s_h2d);
+            }
+            at += got;
+            issued[b] = at;
+            eof = got < want;
+        }
+        cudaStreamSynchronize(ps.s_h2d);
+        std::lock_guard<std::mutex> lk(mu);
+        resident = at;
+        in_done = true;
+        in_eof = eof || lent;  // a contiguous source has nothing beyond its bytes
+        cv.notify_all();
+    };
+
+    auto stage_out = [&]() {
+        cudaSetDevice(device);
+        for (;;) {
+            const int i = out_q.pop();
+            if (i == kEnd) break;
+            if (slots[i].out_len && fail.load() == HUF_ERROR_SUCCESS) {
+                double t0 = now_s();
+                if (cudaEventSynchronize(ps.ev_d2h[i]) != cudaSuccess) {
+                    cudaGetLastError();
+                    set_fail(HUF_ERROR_FATAL);
+                } else {
+                    tm.d2h_wait += now_s() - t0;
+                    t0 = now_s();
+                    huf_error_t e = sink_deliver(*dst, ps.pin_out[i].p, slots[i].out_len);
+                    tm.deliver += now_s() - t0;
+                    if (e != HUF_ERROR_SUCCESS) set_fail(e);
+                }
+            }
+            free_q.push(i);
+        }
+    };
+
+    uint64_t done_in = 0;       // compressed bytes of the blocks decoded so far
+    uint64_t npass = 0;
+    huf_error_t result = HUF_ERROR_SUCCESS;
+
+    auto stage_kernels = [&]() {
+        double ratio = 1.3;     // decoded bytes per compressed byte, learnt from the passes
+        for (;;) {
+            if (fail.load() != HUF_ERROR_SUCCESS) break;
+            // ---- wait for enough resident bytes for a worthwhile pass
+            uint64_t have;
+            bool all_in, eof;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return in_done || resident >= done_in + span + c->dec_margin; });
+                have = resident;
+                all_in = in_done;
+                eof = in_eof;
+            }
+            if (fail.load() != HUF_ERROR_SUCCESS) break;
+            // ---- blocks may start in [done_in, stop): everything while bytes are still arriving
+            // except a margin in which a block would not be whole yet
+            uint64_t stop = length;
+            if (!all_in) {
+                const uint64_t safe = have > c->dec_margin ? have - c->dec_margin : 0;
+                if (safe < stop) stop = safe;
+            }
+            // keep the pass inside what an output slot holds
+            const uint64_t fit = (uint64_t)((double)out_cap * 0.85 / ratio);
+            if (stop > done_in + fit && fit >= (1u << 16)) stop = done_in + fit;
+            if (stop <= done_in) {
+                if (all_in) stop = length;  // (cannot happen with a margin; be safe)
+                else continue;
+            }
+            const int i = free_q.pop();
+            const double t0 = now_s();
+            const uint64_t cap = ps.d_out[i].cap < ps.pin_out[i].cap ? ps.d_out[i].cap : ps.pin_out[i].cap;
+            huf_error_t e = huf_b200_decode_async_at(c, ps.d_stream.p, have, stop, done_in, ps.d_out[i].p, cap,
+                                                     HUF_B200_STREAM_PRIVATE);
+            uint64_t n = 0, reached = done_in;
+            if (e == HUF_ERROR_SUCCESS) e = huf_b200_decode_finish(c, &n, &reached);
+            tm.kern += now_s() - t0;
+            npass++;
+            slots[i].out_len = n;
+            if (n) {
+                cudaMemcpyAsync(ps.pin_out[i].p, ps.d_out[i].p, n, cudaMemcpyDeviceToHost, ps.s_d2h);
+                cudaEventRecord(ps.ev_d2h[i], ps.s_d2h);
+            }
+            out_q.push(i);  // (also returns an unused slot)
+            const bool progressed = reached > done_in;
+            if (progressed) ratio = 0.5 * ratio + 0.5 * ((double)n / (double)(reached - done_in));
+            if (ratio < 0.05) ratio = 0.05;
+            done_in = reached;
+            if (e == HUF_ERROR_SUCCESS) {
+                if (done_in >= length) break;
+                continue;  // (a pass that stopped at `stop` < length: go on from there)
+            }
+            if (e == HUF_ERROR_MEMORY_ALLOCATION) {
+                // an output slot was the limit: resume behind what was delivered; a block that does
+                // not fit an empty slot needs bigger slots
+                if (!progressed) {
+                    const uint64_t need = c->h_result[7] + 4096;  // largest orig_len among the candidates
+                    if (need <= out_cap) {
+                        result = e;
+                        break;
+                    }
+                    // slots in flight must drain before their buffers are replaced
+                    int held[kSlots];
+                    for (int q = 0; q < kSlots; q++) held[q] = free_q.pop();
+                    cudaStreamSynchronize(ps.s_d2h);
+                    huf_error_t e2 = HUF_ERROR_SUCCESS;
+                    for (int q = 0; q < kSlots && e2 == HUF_ERROR_SUCCESS; q++) {
+                        e2 = reserve_device(ps.d_out[q], need);
+                        if (e2 == HUF_ERROR_SUCCESS) e2 = reserve_pinned(ps.pin_out[q], need);
+                    }
+                    for (int q = 0; q < kSlots; q++) free_q.push(held[q]);
+                    if (e2 != HUF_ERROR_SUCCESS) {
+                        result = e2;
+                        break;
+                    }
+                    out_cap = need;
+                }
+                continue;
+            }
+            if (e == HUF_ERROR_READ_WRITE) {
+                // the failing block may simply continue in bytes that are not resident yet
+                if (!all_in) {
+                    // wait for more bytes than this pass saw; keep a wider margin from now on
+                    const uint64_t ext = c->h_result[9];  // largest block extent seen
+                    if (2 * ext + 65536 > c->dec_margin) c->dec_margin = 2 * ext + 65536;
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return in_done || resident > have; });
+                    continue;
+                }
+                if (!eof) {
+                    // pull source: the in-stage is finished, so this thread pulls more itself
+                    const uint64_t more = have > 65536 ? have : 65536;
+                    huf_error_t e2 = reserve_device(ps.d_stream, have + more + 64, true, have);
+                    uint64_t got = 0, at = have;
+                    while (e2 == HUF_ERROR_SUCCESS && at < have + more) {
+                        const uint64_t want = have + more - at < ps.pin_in[0].cap ? have + more - at : ps.pin_in[0].cap;
+                        e2 = source_fill(*src, at, ps.pin_in[0].p, want, &got);
+                        if (e2 != HUF_ERROR_SUCCESS || !got) break;
+                        cudaMemcpyAsync(ps.d_stream.p + at, ps.pin_in[0].p, got, cudaMemcpyHostToDevice, ps.s_h2d);
+                        cudaStreamSynchronize(ps.s_h2d);
+                        at += got;
+                        if (got < want) break;
+                    }
+                    if (e2 != HUF_ERROR_SUCCESS) {
+                        result = e2;
+                        break;
+                    }
+                    std::lock_guard<std::mutex> lk(mu);
+                    in_eof = at < have + more;
+                    if (at > resident) {
+                        resident = at;
+                        continue;
+                    }
+                }
+            }
+            result = e;
+            break;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop_in = true;
+        }
+        out_q.push(kEnd);
+    };
+
+    if (nspans <= 1) {
+        stage_in();
+        stage_kernels();
+        stage_out();
+    } else {
+        std::thread t_in(stage_in), t_out(stage_out);
+        stage_kernels();
+        t_in.join();
+        t_out.join();
+    }
+    cudaStreamSynchronize(ps.s_h2d);
+    cudaStreamSynchronize(ps.s_d2h);
+    if (consumed) *consumed = done_in;
+    if (debug_on() && planned >= (1u << 20)) {
+        const double dt = now_s() - t_start;
+        fprintf(stderr,
+                "huf_b200: decode_host %.1f MiB in %.1f ms (%.2f GB/s compressed): %llu passes; busy ms: fill %.1f kernels+sync %.1f "
+                "d2h wait %.1f deliver %.1f\n",
+                planned / 1048576.0, dt * 1e3, planned / dt / 1e9, (unsigned long long)npass, tm.fill * 1e3, tm.kern * 1e3,
+                tm.d2h_wait * 1e3, tm.deliver * 1e3);
+    }
+    const huf_error_t e = (huf_error_t)fail.load();
+    return e != HUF_ERROR_SUCCESS ? e : result;
 }
 
 }  // extern "C"

@@ -382,8 +382,9 @@ inline auto max(A a, B b) -> typename std::common_type<A, B>::type
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
-enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1 };
+enum { cudaHostAllocDefault = 0, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 struct cudaDeviceProp {
     int major = 10, minor = 0, multiProcessorCount = 1;
@@ -411,6 +412,8 @@ inline cudaError_t cudaMalloc(T **p, size_t n)
 }
 template <typename T>
 inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <typename T>
+inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { *p = (T *)malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
@@ -418,6 +421,8 @@ inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyK
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 typedef void *cudaEvent_t;
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }

@@ -232,3 +232,139 @@ def test_emu_decode_with_block_index_hint(emu, harness):
     finally:
         enc.close()
         dec.close()
+
+
+# ---- host lanes (huf_b200_encode_host / huf_b200_decode_host): spans, stage threads, streams ----
+
+class _CallbackStream:
+    """A user-supplied huf_read_writer_t (legal per reference include/huffman/io.h:11-21): read
+    hands out at most `chunk` bytes per call, write collects."""
+
+    def __init__(self, data: bytes = b"", chunk: int = 1000):
+        from libhuffman_b200.capi import READ_FN, WRITE_FN, ReadWriter
+        self.src = data
+        self.pos = 0
+        self.chunk = chunk
+        self.out = bytearray()
+
+        def _read(_stream, buf, count_p):
+            n = min(count_p[0], self.chunk, len(self.src) - self.pos)
+            C.memmove(buf, self.src[self.pos:self.pos + n], n)
+            self.pos += n
+            count_p[0] = n
+            return 0
+
+        def _write(_stream, buf, count):
+            self.out += C.string_at(buf, count)
+            return 0
+
+        self._r, self._w = READ_FN(_read), WRITE_FN(_write)
+        self.rw = ReadWriter(None, self._w, self._r)
+
+
+def _codec_call(lib, fn, length, blocksize, reader, writer):
+    from libhuffman_b200.capi import Config
+    cfg = Config(length=length, blocksize=blocksize, reader=reader, writer=writer)
+    return getattr(lib.dll, fn)(C.byref(cfg))
+
+
+@pytest.fixture
+def small_spans(monkeypatch):
+    """Many spans out of a small input: every stage thread and slot hand-over of the host lanes runs."""
+    monkeypatch.setenv("HUF_B200_SPAN_BYTES", "8192")
+
+
+def test_emu_host_lane_many_spans(emu, harness, small_spans):
+    data = datagen.zipf(70000 + 123, 200, seed=31)
+    for bs in (4096, 1000, 30000):   # 2 blocks per span / 8 per span / a block larger than a span
+        want = harness.oracle_encode(data, bs)
+        rc, got = emu.encode(data, bs)
+        assert rc == 0 and got == want, bs
+        rc, back = emu.decode(want)
+        assert (rc, back) == (0, data), bs
+    # the reader runs dry inside the 6th span: whole blocks before it, then READ_WRITE (Q11)
+    rc, got = emu.encode(data[:45000], 4096, length=70000)
+    assert rc == 3 and got == harness.oracle_encode(data[:45000 // 4096 * 4096], 4096)
+    # errors in a late span keep the output of the blocks before them (src/decoder.c:218-276)
+    stream = harness.oracle_encode(data, 4096)
+    rc_o, out_o, _ = harness.oracle_decode(stream[:-700])
+    rc, got = emu.decode(stream[:-700])
+    assert rc == rc_o == 3 and got == out_o
+    bad = bytearray(stream)
+    bad[len(bad) * 3 // 4] ^= 0x10
+    rc_o, out_o, _ = harness.oracle_decode(bytes(bad))
+    rc, got = emu.decode(bytes(bad))
+    assert rc == rc_o and (rc != 0 or got == out_o)
+
+
+def test_emu_host_lane_callback_and_fd_streams(emu, harness, small_spans, tmp_path):
+    """Readers/writers that are not huf_memopen streams go through the pull/push side of the lanes."""
+    data = datagen.english_text(50000, seed=8)
+    bs = 3000
+    want = harness.oracle_encode(data, bs)
+    src, dst = _CallbackStream(data, chunk=777), _CallbackStream()
+    assert _codec_call(emu, "huf_encode", len(data), bs, C.pointer(src.rw), C.pointer(dst.rw)) == 0
+    assert bytes(dst.out) == want
+    # decode: the reader holds more than `length`; the last block continues past it and the bytes
+    # behind that block stay unread (the reference pulls what a block needs, src/decoder.c:218-261)
+    src, dst = _CallbackStream(want + b"trailing", chunk=5000), _CallbackStream()
+    assert _codec_call(emu, "huf_decode", len(want) - 100, 0, C.pointer(src.rw), C.pointer(dst.rw)) == 0
+    assert bytes(dst.out) == data
+    # fd streams (huf_fdopen), file to file
+    from libhuffman_b200.capi import ReadWriter
+    import os
+    fin, fmid, fout = (str(tmp_path / n) for n in ("in", "mid", "out"))
+    open(fin, "wb").write(data)
+    emu.dll.huf_fdopen.argtypes = [C.POINTER(C.POINTER(ReadWriter)), C.c_int]
+    for a, b, fn, length, blk in ((fin, fmid, "huf_encode", len(data), bs), (fmid, fout, "huf_decode", len(want), 0)):
+        fa, fb = os.open(a, os.O_RDONLY), os.open(b, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+        ra, rb = C.POINTER(ReadWriter)(), C.POINTER(ReadWriter)()
+        assert emu.dll.huf_fdopen(C.byref(ra), fa) == 0 and emu.dll.huf_fdopen(C.byref(rb), fb) == 0
+        assert _codec_call(emu, fn, length, blk, ra, rb) == 0
+        emu.dll.huf_fdclose(C.byref(ra))
+        emu.dll.huf_fdclose(C.byref(rb))
+        os.close(fa)
+        os.close(fb)
+    assert open(fmid, "rb").read() == want and open(fout, "rb").read() == data
+
+
+def test_emu_decode_length_beyond_data(emu, harness):
+    """`length` larger than the readable bytes with the data ending on a block
+    boundary, and an empty reader, used to spin in the restart loop; the reference fails on the
+    read of the next header with HUF_ERROR_READ_WRITE (src/decoder.c:220-229)."""
+    data = datagen.english_text(1000, seed=2)
+    stream = harness.oracle_encode(data, 400)
+    rc_o, out_o, _ = harness.oracle_decode(stream, len(stream) + 10)
+    rc, got = emu.decode(stream, length=len(stream) + 10)
+    assert (rc, got) == (rc_o, out_o) == (3, data)
+    rc, got = emu.decode(b"", length=10)
+    assert (rc, got) == (3, b"")
+    # the second decompress() of one HuffmanDecompressor: length counts consumed bytes again (P2)
+    with emu.memstream(len(stream)) as src, emu.memstream(64) as dst:
+        src.write(stream)
+        assert _codec_call(emu, "huf_decode", len(stream), 0, src.rw, dst.rw) == 0
+        assert _codec_call(emu, "huf_decode", len(stream), 0, src.rw, dst.rw) == 3
+        assert dst.getvalue() == data
+
+
+def test_emu_failed_async_leaves_context_usable(emu, harness):
+    """an *_async call that fails before everything is enqueued must not
+    leave the context pending."""
+    data = datagen.zipf(9000, 100, seed=3)
+    codec = DeviceCodec(emu)
+    try:
+        src = C.create_string_buffer(data, len(data))
+        cap = codec.encode_bound(len(data), 1 << 40)
+        dst = C.create_string_buffer(cap)
+        # nspb does not fit 32 bits: INVALID_ARGUMENT from inside encode_async
+        with pytest.raises(Exception):
+            codec.encode_async(C.addressof(src), len(data), 1 << 50, C.addressof(dst), cap)
+        out = C.create_string_buffer(len(data) + 64)
+        stream = harness.oracle_encode(data, 4096)
+        sbuf = C.create_string_buffer(stream, len(stream) + 16)
+        codec.decode_async(C.addressof(sbuf), len(stream), len(stream), C.addressof(out), len(data) + 64)
+        assert codec.decode_finish() == (0, len(data), len(stream))
+        codec.encode_async(C.addressof(src), len(data), 4096, C.addressof(dst), cap)
+        assert dst.raw[:codec.encode_finish()] == stream
+    finally:
+        codec.close()
