@@ -23,8 +23,21 @@
 #include <thread>
 #include <vector>
 
+extern "C" void huf__copy_stream(void *dst, const void *src, size_t n);  // csrc/host/ntcopy.c
+
 namespace hufb200 {
 namespace pipe {
+
+// HUF_B200_NT_COPY=0 switches the staging copies back to plain memcpy (measurement aid).
+inline void stage_copy(void *dst, const void *src, size_t n)
+{
+    static const bool nt = [] {
+        const char *e = getenv("HUF_B200_NT_COPY");
+        return !(e && e[0] == '0');
+    }();
+    if (nt) huf__copy_stream(dst, src, n);
+    else memcpy(dst, src, n);
+}
 
 inline double now_s()
 {
@@ -54,7 +67,7 @@ public:
     {
         constexpr uint64_t kSlice = 2ull << 20;
         if (bytes < 2 * kSlice || nthreads_ == 0) {
-            memcpy(dst, src, bytes);
+            stage_copy(dst, src, bytes);
             return;
         }
         Job job;
@@ -94,7 +107,8 @@ private:
     {
         unsigned hc = std::thread::hardware_concurrency();
         const char *env = getenv("HUF_B200_COPY_THREADS");
-        unsigned want = env ? (unsigned)atoi(env) : 12u;
+        // default: all cores but two (the stage threads of a call need some), at most 16
+        unsigned want = env ? (unsigned)atoi(env) : (hc > 3 ? (hc - 2 > 16 ? 16u : hc - 2) : 1u);
         if (hc && want > hc) want = hc;
         if (want < 1) want = 1;
         nthreads_ = want - 1;  // the calling thread is one of the workers
@@ -118,7 +132,7 @@ private:
             if (i >= job.nslices) return;
             const uint64_t at = i * job.slice;
             const uint64_t len = job.bytes - at < job.slice ? job.bytes - at : job.slice;
-            memcpy(job.dst + at, job.src + at, len);
+            stage_copy(job.dst + at, job.src + at, len);
             if (job.done.fetch_add(1) + 1 == job.nslices) {
                 std::lock_guard<std::mutex> lk(mu_);
                 done_cv_.notify_all();
@@ -149,7 +163,7 @@ private:
             lk.unlock();
             const uint64_t at = i * job->slice;
             const uint64_t len = job->bytes - at < job->slice ? job->bytes - at : job->slice;
-            memcpy(job->dst + at, job->src + at, len);
+            stage_copy(job->dst + at, job->src + at, len);
             const bool last = job->done.fetch_add(1) + 1 == job->nslices;
             lk.lock();
             if (last) done_cv_.notify_all();
@@ -194,7 +208,7 @@ private:
 
 // ---- buffers cached across calls (one set per device) -------------------------------------------
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 6;   // spans in flight at most (fill, H2D, kernels, D2H, deliver overlap)
 constexpr int kEnd = -1;
 
 struct Buf {
@@ -283,6 +297,16 @@ struct PipeState {
 
 // Bytes per span: HUF_B200_SPAN_MIB (default 32), or HUF_B200_SPAN_BYTES for tests that want
 // many spans out of a small input.  Read at every call (cheap) so a process can change it.
+// Slots used by a call: HUF_B200_SLOTS (2..kSlots, default 5).
+inline int slot_count()
+{
+    const char *env = getenv("HUF_B200_SLOTS");
+    int n = env ? atoi(env) : 5;
+    if (n < 2) n = 2;
+    if (n > kSlots) n = kSlots;
+    return n;
+}
+
 inline uint64_t span_bytes()
 {
     if (const char *env = getenv("HUF_B200_SPAN_BYTES")) {

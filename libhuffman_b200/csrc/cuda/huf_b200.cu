@@ -861,7 +861,7 @@ huf_error_t huf_b200_encode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
     if (!span) span = bs;
     if (span > length) span = length;
     const uint64_t nspans = (length + span - 1) / span;
-    const int nslots = nspans < (uint64_t)kSlots ? (int)nspans : kSlots;
+    const int nslots = nspans < (uint64_t)slot_count() ? (int)nspans : slot_count();
     const uint64_t out_cap = huf_b200_encode_bound(span, bs);
     for (int i = 0; i < nslots; i++) {
         HUF_TRY_CXX(reserve_pinned(ps.pin_in[i], span));
@@ -1029,7 +1029,8 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
     for (int i = 0; i < 2; i++) HUF_TRY_CXX(reserve_pinned(ps.pin_in[i], span < planned ? span : planned));
     // output slots: a pass decodes about one span of input; the capacity adapts to the data
     uint64_t out_cap = 2 * span;
-    for (int i = 0; i < kSlots; i++) {
+    const int nslots = nspans <= 1 ? 1 : (slot_count() > 4 ? 4 : slot_count());
+    for (int i = 0; i < nslots; i++) {
         HUF_TRY_CXX(reserve_device(ps.d_out[i], out_cap));
         HUF_TRY_CXX(reserve_pinned(ps.pin_out[i], out_cap));
     }
@@ -1039,7 +1040,7 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
     };
     Slot slots[kSlots];
     Chan<int> free_q, out_q;
-    for (int i = 0; i < kSlots; i++) free_q.push(i);
+    for (int i = 0; i < nslots; i++) free_q.push(i);
     std::atomic<int> fail{HUF_ERROR_SUCCESS};
     StageTimes tm;
     const double t_start = now_s();
@@ -1188,14 +1189,14 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
                     }
                     // slots in flight must drain before their buffers are replaced
                     int held[kSlots];
-                    for (int q = 0; q < kSlots; q++) held[q] = free_q.pop();
+                    for (int q = 0; q < nslots; q++) held[q] = free_q.pop();
                     cudaStreamSynchronize(ps.s_d2h);
                     huf_error_t e2 = HUF_ERROR_SUCCESS;
-                    for (int q = 0; q < kSlots && e2 == HUF_ERROR_SUCCESS; q++) {
+                    for (int q = 0; q < nslots && e2 == HUF_ERROR_SUCCESS; q++) {
                         e2 = reserve_device(ps.d_out[q], need);
                         if (e2 == HUF_ERROR_SUCCESS) e2 = reserve_pinned(ps.pin_out[q], need);
                     }
-                    for (int q = 0; q < kSlots; q++) free_q.push(held[q]);
+                    for (int q = 0; q < nslots; q++) free_q.push(held[q]);
                     if (e2 != HUF_ERROR_SUCCESS) {
                         result = e2;
                         break;

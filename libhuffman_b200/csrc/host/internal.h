@@ -31,6 +31,9 @@ huf_error_t huf__memstream_reserve(huf_memstream_t *m, size_t extra, uint8_t **w
 /* Read exactly up to `want` bytes by calling rw->read until it reports end of data. */
 huf_error_t huf__read_fully(huf_read_writer_t *rw, void *dst, size_t want, size_t *got);
 
+/* memcpy with streaming stores for large staging copies (ntcopy.c). */
+void huf__copy_stream(void *dst, const void *src, size_t n);
+
 /* Process-wide GPU context used by huf_encode/huf_decode (created lazily). */
 huf_error_t huf__codec_context(huf_b200_ctx_t **ctx);
 void huf__codec_context_unlock(void);
