@@ -114,6 +114,22 @@ huf_error_t huf_b200_decode_async_at(huf_b200_ctx_t *ctx, const void *d_in, uint
                                      uint64_t length, uint64_t first, void *d_out,
                                      uint64_t out_capacity, void *stream);
 
+/* Byte-range decode, the unit of a multi-GPU decode of ONE stream (the
+ * reference walks the stream serially, src/decoder.c:218-276): decode every block that STARTS in
+ * [start, stop) of d_in.  `start` need not be a block start -- the first block is the first
+ * header candidate at or behind it, unless start_is_block says that `start` is one (the
+ * stream start, or a chain end the caller has proven) --
+ * and the last block may reach past `stop` (the caller supplies that overlap in `avail`).
+ * _finish returns where the first block was found (*first, ~0 when no block starts in the
+ * range), where the chain of decoded blocks ends (*end) and the decoded bytes (in d_out from
+ * offset 0).  Neighbouring ranges are stitched by the caller: range g is consistent when
+ * end(g-1) == first(g); the decoded slabs concatenate in range order. */
+huf_error_t huf_b200_decode_range_async(huf_b200_ctx_t *ctx, const void *d_in, uint64_t avail,
+                                        uint64_t start, uint64_t stop, int start_is_block,
+                                        void *d_out, uint64_t out_capacity, void *stream);
+huf_error_t huf_b200_decode_range_finish(huf_b200_ctx_t *ctx, uint64_t *first, uint64_t *end,
+                                         uint64_t *out_len);
+
 /* ---- host-buffer lanes ----------------------------------------------------------------------
  * What huf_encode / huf_decode run below their stream objects (reference src/io.c:9-226,
  * src/bufio.c:149-287): the bytes come from a source and go to a sink in HOST memory, and the
@@ -151,6 +167,28 @@ huf_error_t huf_b200_encode_host(huf_b200_ctx_t *ctx, const huf_b200_source_t *s
  * compressed bytes of the whole blocks decoded. */
 huf_error_t huf_b200_decode_host(huf_b200_ctx_t *ctx, const huf_b200_source_t *src, uint64_t length,
                                  const huf_b200_sink_t *dst, uint64_t *consumed);
+
+/* Several GPUs in one call.  ctxs[0..ndev) are contexts on different devices.
+ * Encode: device g takes the contiguous block range [g*B/ndev, (g+1)*B/ndev) of the input
+ * (blocks are independent, src/encoder.c:345,360-373), the slabs are placed in `dst` at the
+ * exclusive scan of their sizes: the result is byte-identical to the one-device stream.
+ * Decode: device g scans the byte range [g*C/ndev, (g+1)*C/ndev) of the ONE stream (plus an
+ * overlap for its last block) and decodes the blocks that start in it; the host validates the
+ * chain across the ranges (end of range g-1 == first block of range g) and concatenates the
+ * decoded slabs; a seam that does not validate falls back to the one-device lane, so results
+ * never depend on the split.  No device-to-device traffic, no collective.  `dst` must be a
+ * lending sink (reserve/commit).  slab_sizes (optional) receives the ndev slab sizes. */
+huf_error_t huf_b200_encode_host_multi(huf_b200_ctx_t *const *ctxs, int ndev, const void *h_in,
+                                       uint64_t length, uint64_t blocksize,
+                                       const huf_b200_sink_t *dst, uint64_t *slab_sizes);
+huf_error_t huf_b200_decode_host_multi(huf_b200_ctx_t *const *ctxs, int ndev, const void *h_in,
+                                       uint64_t avail, uint64_t length, const huf_b200_sink_t *dst,
+                                       uint64_t *consumed);
+/* Plan of a byte-range decode (see huf_b200_decode_range_async): decoded size of the blocks
+ * whose headers the scan finds in [start, stop). */
+huf_error_t huf_b200_decode_range_plan(huf_b200_ctx_t *ctx, const void *d_in, uint64_t avail,
+                                       uint64_t start, uint64_t stop, int start_is_block,
+                                       uint64_t *out_len, uint64_t *nblocks, void *stream);
 
 /* Counters for benches/tests: kernels launched by the last *_async call. */
 uint64_t huf_b200_last_launch_count(const huf_b200_ctx_t *ctx);

@@ -172,6 +172,10 @@ class B200Lib(HuffmanCLib):
         d.huf_b200_encode_block_offsets.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         d.huf_b200_decode_async.argtypes = [vp, vp, u64, u64, vp, u64, vp]
         d.huf_b200_decode_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        d.huf_b200_decode_async_at.argtypes = [vp, vp, u64, u64, u64, vp, u64, vp]
+        d.huf_b200_decode_range_async.argtypes = [vp, vp, u64, u64, u64, C.c_int, vp, u64, vp]
+        d.huf_b200_decode_range_plan.argtypes = [vp, vp, u64, u64, u64, C.c_int, C.POINTER(u64), C.POINTER(u64), vp]
+        d.huf_b200_decode_range_finish.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         d.huf_b200_decode_plan.argtypes = [vp, vp, u64, u64, C.POINTER(u64), C.POINTER(u64), vp]
         d.huf_b200_last_launch_count.restype = u64
         d.huf_b200_last_launch_count.argtypes = [vp]
@@ -187,6 +191,8 @@ class B200Lib(HuffmanCLib):
         for name in ("huf_b200_ctx_create", "huf_b200_ctx_destroy", "huf_b200_ctx_set_option",
                      "huf_b200_encode_async", "huf_b200_encode_finish", "huf_b200_encode_block_offsets",
                      "huf_b200_decode_async", "huf_b200_decode_finish", "huf_b200_decode_plan",
+                     "huf_b200_decode_async_at", "huf_b200_decode_range_async", "huf_b200_decode_range_finish",
+                     "huf_b200_decode_range_plan",
                      "huf_b200_dev_alloc", "huf_b200_dev_free", "huf_b200_copy_h2d", "huf_b200_copy_d2h"):
             getattr(d, name).restype = C.c_int
 
@@ -249,6 +255,33 @@ class DeviceCodec:
         used = C.c_uint64()
         rc = self.lib.dll.huf_b200_decode_finish(self.ctx, C.byref(n), C.byref(used))
         return rc, n.value, used.value
+
+    def decode_range_async(self, d_in: int, avail: int, start: int, stop: int, d_out: int, out_cap: int,
+                           stream: int = 0, start_is_block: bool | None = None) -> None:
+        """Decode the blocks that start in [start, stop) of the stream (multi-GPU decode unit).
+        start_is_block: `start` is a known block start (default: only when start == 0)."""
+        if start_is_block is None:
+            start_is_block = start == 0
+        self.lib.check(self.lib.dll.huf_b200_decode_range_async(self.ctx, d_in, avail, start, stop,
+                                                                int(start_is_block), d_out, out_cap, stream),
+                       "huf_b200_decode_range_async")
+
+    def decode_range_plan(self, d_in: int, avail: int, start: int, stop: int, stream: int = 0,
+                          start_is_block: bool | None = None) -> int:
+        """Decoded size of the blocks whose headers the scan finds in [start, stop)."""
+        if start_is_block is None:
+            start_is_block = start == 0
+        n = C.c_uint64()
+        self.lib.check(self.lib.dll.huf_b200_decode_range_plan(self.ctx, d_in, avail, start, stop,
+                                                               int(start_is_block), C.byref(n), None, stream),
+                       "huf_b200_decode_range_plan")
+        return n.value
+
+    def decode_range_finish(self) -> tuple[int, int, int, int]:
+        """Returns (huf_error_t, offset of the first block found or None, chain end, decoded bytes)."""
+        first, end, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        rc = self.lib.dll.huf_b200_decode_range_finish(self.ctx, C.byref(first), C.byref(end), C.byref(n))
+        return rc, (None if first.value == 2 ** 64 - 1 else first.value), end.value, n.value
 
     def decode_plan(self, d_in: int, avail: int, length: int, stream: int = 0) -> tuple[int, int]:
         n = C.c_uint64()

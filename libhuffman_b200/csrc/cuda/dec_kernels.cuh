@@ -43,8 +43,10 @@ struct DecArgs {
     const uint8_t *in;
     uint64_t avail;      // readable bytes
     uint64_t length;     // blocks may start while offset < length
-    uint64_t first;      // proven block start this pass begins at
+    uint64_t first;      // offset this pass begins at: a proven block start (first_proven), or
+                         // just the lower bound of the byte range whose blocks are wanted
     uint64_t out_base;   // output bytes already produced before `first`
+    uint32_t first_proven;
     uint8_t *out;
     uint64_t out_cap;
     uint32_t accept_1025;
@@ -71,7 +73,13 @@ struct DecArgs {
                            // [9] largest block extent (header + payload bytes) seen
                            // [10] blocks the fast lane left to k_decode_slow
                            // [11] work counter of k_decode (next candidate to hand out)
+                           // [12] offset of the first candidate of the pass (~0: none)
 };
+
+// The header scan walks 16-byte aligned chunks from the aligned offset at or in front of `first`
+// (so that its vector loads stay aligned whatever `first` is); offsets in front of `first` are
+// never candidates.
+__device__ __host__ __forceinline__ uint64_t find_base(uint64_t first) { return first & ~uint64_t(15); }
 
 // ------------------------------------------------------------------------------------------
 // byte-granular, bounds-checked readers
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
     const uint64_t chunk = (uint64_t)blockIdx.x * kFindWarps + warp_in_cta();
     if (chunk >= a.nchunks) return;
     const uint64_t lim = a.length < a.avail ? a.length : a.avail;  // starts must be < lim
-    const uint64_t c0 = a.first + chunk * kFindChunk;
+    const uint64_t c0 = find_base(a.first) + chunk * kFindChunk;
     if (MODE == 1 && a.chunk_cnt[chunk] == 0) return;
 
     uint64_t wr = MODE == 1 ? a.chunk_off[chunk] : 0;
@@ -188,16 +196,17 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
                 while (pre) {
                     const int i = __ffs(pre) - 1;
                     pre &= pre - 1;
-                    if (o0 + i < lim && header_plausible(a, o0 + i)) mask |= 1u << i;
+                    if (o0 + i >= a.first && o0 + i < lim && header_plausible(a, o0 + i)) mask |= 1u << i;
                 }
             } else {
                 for (int i = 0; i < 16; i++) {
                     const uint64_t o = o0 + i;
-                    if (o < lim && o + 12 <= a.avail && a.in[o + 11] == 1 && header_plausible(a, o))
+                    if (o >= a.first && o < lim && o + 12 <= a.avail && a.in[o + 11] == 1 && header_plausible(a, o))
                         mask |= 1u << i;
                 }
             }
-            if (o0 == a.first) mask |= 1u;  // the proven start is always block 0
+            // a proven start is always block 0
+            if (a.first_proven && a.first >= o0 && a.first < o0 + 16 && a.first < lim) mask |= 1u << (uint32_t)(a.first - o0);
         }
         const uint32_t n = __popc(mask);
         total += n;
@@ -236,7 +245,7 @@ __global__ void k_compact(DecArgs a)
     if (chunk >= a.nchunks) return;
     const uint32_t n = min(a.chunk_cnt[chunk], kFindSlots);
     const uint64_t at = a.chunk_off[chunk];
-    const uint64_t c0 = a.first + chunk * kFindChunk;
+    const uint64_t c0 = find_base(a.first) + chunk * kFindChunk;
     for (uint32_t i = 0; i < n; i++) {
         if (at + i < a.max_cand) a.cand[at + i] = c0 + a.slots[chunk * kFindSlots + i];
     }
@@ -251,7 +260,7 @@ __global__ void k_hint(DecArgs a, const uint64_t *__restrict__ hint, uint64_t n)
     const uint64_t lim = a.length < a.avail ? a.length : a.avail;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && i < a.max_cand) {
-        const uint64_t off = i == 0 ? a.first : hint[i];  // the proven start is always block 0
+        const uint64_t off = i == 0 ? a.first : hint[i];  // the proven start is always block 0 (hints are only used with one)
         a.cand[i] = off < lim ? off : lim;
     }
     if (i == 0) {
@@ -1030,6 +1039,8 @@ __global__ void __launch_bounds__(kScanThreads) k_verify(DecArgs a)
             reached = n ? a.end_off[n - 1] : a.first;
             produced = a.out_off[n];
         }
+        if (!a.first_proven && n == 0) done = 1;  // no block starts in the byte range: nothing to do
+        a.result[12] = n ? a.cand[0] : ~0ull;
         if (!done && reached >= a.length) done = 1;
         if (!done && reached >= a.avail) {
             // `length` asks for another block but the readable bytes end here: the reference

@@ -123,6 +123,7 @@ struct huf_b200_ctx {
     // decode call in flight
     bool dec_pending = false;
     uint64_t dec_first = 0;         // offset the pending decode call started at
+    uint64_t dec_first_cand = ~0ull;  // offset of the first block the call found (range mode)
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
     const uint64_t *hint_off = nullptr;  // optional block index for the next decode (device pointer)
@@ -507,18 +508,20 @@ namespace {
 
 // Enqueue one speculative pass starting at the proven block start `first`.
 huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool plan_only,
-                        uint64_t max_cand_hint)
+                        uint64_t max_cand_hint, bool first_proven = true)
 {
     DecArgs &a = c->dec;
     cudaStream_t st = c->cur;
     a.first = first;
+    a.first_proven = first_proven ? 1u : 0u;
     a.out_base = out_base;
     a.accept_1025 = (uint32_t)c->accept_1025;
     a.count_only = plan_only ? 1u : 0u;
 
     const uint64_t lim = a.length < a.avail ? a.length : a.avail;
     const uint64_t span = lim > first ? lim - first : 0;
-    a.nchunks = (span + kFindChunk - 1) / kFindChunk;
+    const uint64_t scan = lim > find_base(first) ? lim - find_base(first) : 0;  // the scan starts aligned
+    a.nchunks = (scan + kFindChunk - 1) / kFindChunk;
     if (!a.nchunks) a.nchunks = 1;
     uint64_t max_cand = max_cand_hint ? max_cand_hint : span / 256 + 1024;
     const bool hinted = c->hint_off && c->hint_n && first == 0 && !plan_only;
@@ -616,9 +619,10 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
 
 }  // namespace
 
-huf_error_t huf_b200_decode_async_at(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
-                                     uint64_t length, uint64_t first, void *d_out,
-                                     uint64_t out_capacity, void *stream)
+namespace {
+huf_error_t decode_start(huf_b200_ctx_t *c, const void *d_in, uint64_t avail, uint64_t length,
+                         uint64_t first, bool first_proven, void *d_out, uint64_t out_capacity,
+                         void *stream)
 {
     if (!c || (!d_in && avail) || (!d_out && out_capacity)) return HUF_ERROR_INVALID_ARGUMENT;
     if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
@@ -636,10 +640,38 @@ huf_error_t huf_b200_decode_async_at(huf_b200_ctx_t *c, const void *d_in, uint64
     a.out = static_cast<uint8_t *>(d_out);
     a.out_cap = out_capacity;
     // (pending only after a successful enqueue, see huf_b200_encode_async)
-    const huf_error_t e = length > first ? dec_enqueue(c, first, 0, false, 0)
+    const huf_error_t e = length > first ? dec_enqueue(c, first, 0, false, 0, first_proven)
                                          : HUF_ERROR_SUCCESS;  // src/decoder.c:218: nothing to consume
     c->dec_first = first;
+    c->dec_first_cand = ~0ull;
     c->dec_pending = e == HUF_ERROR_SUCCESS;
+    return e;
+}
+}  // namespace
+
+huf_error_t huf_b200_decode_async_at(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                     uint64_t length, uint64_t first, void *d_out,
+                                     uint64_t out_capacity, void *stream)
+{
+    return decode_start(c, d_in, avail, length, first, true, d_out, out_capacity, stream);
+}
+
+huf_error_t huf_b200_decode_range_async(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                        uint64_t start, uint64_t stop, int start_is_block,
+                                        void *d_out, uint64_t out_capacity, void *stream)
+{
+    if (stop > avail) stop = avail;
+    return decode_start(c, d_in, avail, stop, start, start_is_block != 0, d_out, out_capacity, stream);
+}
+
+huf_error_t huf_b200_decode_range_finish(huf_b200_ctx_t *c, uint64_t *first, uint64_t *end,
+                                         uint64_t *out_len)
+{
+    if (!first || !end || !out_len) return HUF_ERROR_INVALID_ARGUMENT;
+    uint64_t reached = 0;
+    const huf_error_t e = huf_b200_decode_finish(c, out_len, &reached);
+    *first = c ? c->dec_first_cand : ~0ull;
+    *end = reached;
     return e;
 }
 
@@ -675,16 +707,17 @@ huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_
             // more headers per chunk than the sparse single-pass scan parks: this stream has
             // tiny blocks; rerun (and keep running) with the exact two-pass scan
             c->dec_dense = true;
-            huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, 0);
+            huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, 0, c->dec.first_proven != 0);
             if (e != HUF_ERROR_SUCCESS) return e;
             continue;
         }
         if (r[6] > c->dec.max_cand) {
             // candidate workspace too small for this stream: rerun the pass with the exact size
-            huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, r[6] + 16);
+            huf_error_t e = dec_enqueue(c, c->dec.first, c->dec.out_base, false, r[6] + 16, c->dec.first_proven != 0);
             if (e != HUF_ERROR_SUCCESS) return e;
             continue;
         }
+        if (c->dec_first_cand == ~0ull) c->dec_first_cand = r[12];  // (restarts begin behind it)
         if (r[9] + 64 > c->dec_stage_want) c->dec_stage_want = r[9] + 64;  // adapt staging to block size
         *out_len = r[4];
         if (consumed) *consumed = r[3];
@@ -700,9 +733,31 @@ huf_error_t huf_b200_decode_finish(huf_b200_ctx_t *c, uint64_t *out_len, uint64_
     }
 }
 
+namespace {
+huf_error_t decode_plan_from(huf_b200_ctx_t *c, const void *d_in, uint64_t avail, uint64_t length,
+                             uint64_t first, bool first_proven, uint64_t *out_len,
+                             uint64_t *nblocks, void *stream);
+}
+
 huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
                                  uint64_t length, uint64_t *out_len, uint64_t *nblocks,
                                  void *stream)
+{
+    return decode_plan_from(c, d_in, avail, length, 0, true, out_len, nblocks, stream);
+}
+
+huf_error_t huf_b200_decode_range_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t avail,
+                                       uint64_t start, uint64_t stop, int start_is_block,
+                                       uint64_t *out_len, uint64_t *nblocks, void *stream)
+{
+    if (stop > avail) stop = avail;
+    return decode_plan_from(c, d_in, avail, stop, start, start_is_block != 0, out_len, nblocks, stream);
+}
+
+namespace {
+huf_error_t decode_plan_from(huf_b200_ctx_t *c, const void *d_in, uint64_t avail, uint64_t length,
+                             uint64_t first, bool first_proven, uint64_t *out_len,
+                             uint64_t *nblocks, void *stream)
 {
     if (!c || !out_len || (!d_in && avail)) return HUF_ERROR_INVALID_ARGUMENT;
     if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
@@ -712,7 +767,7 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
     c->launches = 0;
     *out_len = 0;
     if (nblocks) *nblocks = 0;
-    if (!length) return HUF_ERROR_SUCCESS;
+    if (length <= first) return HUF_ERROR_SUCCESS;
     c->dec_dense = false;
     DecArgs &a = c->dec;
     memset(&a, 0, sizeof(a));
@@ -721,7 +776,7 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
     a.length = length;
     uint64_t hint = 0;
     for (;;) {
-        huf_error_t e = dec_enqueue(c, 0, 0, true, hint);
+        huf_error_t e = dec_enqueue(c, first, 0, true, hint, first_proven);
         if (e != HUF_ERROR_SUCCESS) return e;
         CU_TRY(cudaStreamSynchronize(c->cur));
         if (c->h_result[8] && !c->dec_dense) {
@@ -742,6 +797,7 @@ huf_error_t huf_b200_decode_plan(huf_b200_ctx_t *c, const void *d_in, uint64_t a
     if (c->h_result[9] + 64 > c->dec_stage_want) c->dec_stage_want = c->h_result[9] + 64;
     return HUF_ERROR_SUCCESS;
 }
+}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // raw device memory helpers
@@ -1274,6 +1330,297 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
     }
     const huf_error_t e = (huf_error_t)fail.load();
     return e != HUF_ERROR_SUCCESS ? e : result;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// several GPUs, one call: contiguous block ranges per device for encode,
+// contiguous byte ranges of the ONE stream per device for decode; only sizes and block
+// positions travel between the device threads, the host places the slabs at the exclusive
+// scan of their sizes.  No device-to-device traffic, no collective.
+// ------------------------------------------------------------------------------------------
+
+namespace {
+
+// One thread per device meets here between the phases of a call.
+class Rendezvous {
+public:
+    explicit Rendezvous(int n) : n_(n) {}
+    void arrive()
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        const uint64_t gen = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            gen_++;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return gen_ != gen; });
+        }
+    }
+
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int n_, count_ = 0;
+    uint64_t gen_ = 0;
+};
+
+// host memory -> device memory through the context's two pinned buffers (fill of piece k+1
+// overlaps the DMA of piece k)
+huf_error_t upload(huf_b200_ctx *c, uint8_t *d_dst, const uint8_t *h_src, uint64_t bytes)
+{
+    using namespace pipe;
+    PipeState &ps = c->pipe;
+    const uint64_t piece = span_bytes();
+    for (int i = 0; i < 2; i++) HUF_TRY_CXX(reserve_pinned(ps.pin_in[i], piece < bytes ? piece : bytes));
+    uint64_t k = 0;
+    for (uint64_t at = 0; at < bytes; at += piece, k++) {
+        const int b = (int)(k & 1);
+        const uint64_t len = bytes - at < piece ? bytes - at : piece;
+        if (k >= 2) CU_TRY(cudaEventSynchronize(ps.ev_h2d[b]));
+        CopyPool::get().copy(ps.pin_in[b].p, h_src + at, len);
+        CU_TRY(cudaMemcpyAsync(d_dst + at, ps.pin_in[b].p, len, cudaMemcpyHostToDevice, ps.s_h2d));
+        CU_TRY(cudaEventRecord(ps.ev_h2d[b], ps.s_h2d));
+    }
+    CU_TRY(cudaStreamSynchronize(ps.s_h2d));
+    return HUF_ERROR_SUCCESS;
+}
+
+// device memory -> host memory, same scheme the other way round
+huf_error_t download(huf_b200_ctx *c, uint8_t *h_dst, const uint8_t *d_src, uint64_t bytes)
+{
+    using namespace pipe;
+    PipeState &ps = c->pipe;
+    const uint64_t piece = span_bytes();
+    for (int i = 0; i < 2; i++) HUF_TRY_CXX(reserve_pinned(ps.pin_out[i], piece < bytes ? piece : bytes));
+    const uint64_t npieces = (bytes + piece - 1) / piece;
+    auto issue = [&](uint64_t k) -> cudaError_t {
+        const uint64_t at = k * piece;
+        const uint64_t len = bytes - at < piece ? bytes - at : piece;
+        cudaError_t e = cudaMemcpyAsync(ps.pin_out[k & 1].p, d_src + at, len, cudaMemcpyDeviceToHost, ps.s_d2h);
+        if (e == cudaSuccess) e = cudaEventRecord(ps.ev_d2h[k & 1], ps.s_d2h);
+        return e;
+    };
+    if (npieces) CU_TRY(issue(0));
+    for (uint64_t k = 0; k < npieces; k++) {
+        const uint64_t at = k * piece;
+        const uint64_t len = bytes - at < piece ? bytes - at : piece;
+        CU_TRY(cudaEventSynchronize(ps.ev_d2h[k & 1]));
+        if (k + 1 < npieces) CU_TRY(issue(k + 1));  // next DMA overlaps this copy
+        CopyPool::get().copy(h_dst + at, ps.pin_out[k & 1].p, len);
+        // (the buffer of piece k is refilled by piece k+2, which is issued after this copy)
+    }
+    return HUF_ERROR_SUCCESS;
+}
+
+}  // namespace
+
+huf_error_t huf_b200_encode_host_multi(huf_b200_ctx_t *const *ctxs, int ndev, const void *h_in,
+                                       uint64_t length, uint64_t blocksize,
+                                       const huf_b200_sink_t *dst, uint64_t *slab_sizes)
+{
+    using namespace pipe;
+    if (!ctxs || ndev < 1 || ndev > 64 || !dst || !dst->reserve || (!h_in && length)) return HUF_ERROR_INVALID_ARGUMENT;
+    if (!length) return HUF_ERROR_SUCCESS;
+    const uint64_t bs = blocksize ? blocksize : length;
+    const uint64_t nblocks = huf_b200_block_count(length, bs);
+    std::vector<uint64_t> size(ndev, 0), off(ndev + 1, 0);
+    std::vector<huf_error_t> err(ndev, HUF_ERROR_SUCCESS);
+    uint8_t *base = nullptr;
+    Rendezvous meet(ndev);
+
+    auto worker = [&](int g) {
+        huf_b200_ctx *c = ctxs[g];
+        // contiguous block range of device g (ranges differ by at most one block)
+        const uint64_t q = nblocks / ndev, r = nblocks % ndev;
+        const uint64_t b_lo = g * q + ((uint64_t)g < r ? g : r), b_hi = b_lo + q + ((uint64_t)g < r ? 1 : 0);
+        const uint64_t lo = b_lo * bs < length ? b_lo * bs : length, hi = b_hi * bs < length ? b_hi * bs : length;
+        const uint64_t n = hi - lo;
+        huf_error_t e = HUF_ERROR_SUCCESS;
+        DeviceGuard guard(c->device);
+        PipeState &ps = c->pipe;
+        if (n) {
+            e = ps.init();
+            if (e == HUF_ERROR_SUCCESS) e = reserve_device(ps.d_in[0], n);
+            if (e == HUF_ERROR_SUCCESS) e = reserve_device(ps.d_out[0], huf_b200_encode_bound(n, bs));
+            if (e == HUF_ERROR_SUCCESS) e = upload(c, ps.d_in[0].p, static_cast<const uint8_t *>(h_in) + lo, n);
+            if (e == HUF_ERROR_SUCCESS)
+                e = huf_b200_encode_async(c, ps.d_in[0].p, n, bs, ps.d_out[0].p, ps.d_out[0].cap, HUF_B200_STREAM_PRIVATE);
+            if (e == HUF_ERROR_SUCCESS) e = huf_b200_encode_finish(c, &size[g]);
+        }
+        err[g] = e;
+        meet.arrive();
+        if (g == 0) {
+            // exclusive scan of the slab sizes: where every slab goes in the one stream
+            bool ok = true;
+            for (int k = 0; k < ndev; k++) {
+                ok = ok && err[k] == HUF_ERROR_SUCCESS;
+                off[k + 1] = off[k] + size[k];
+            }
+            if (ok) {
+                void *p = nullptr;
+                const huf_error_t e2 = dst->reserve(dst->arg, off[ndev], &p);
+                if (e2 != HUF_ERROR_SUCCESS || !p) err[0] = e2 != HUF_ERROR_SUCCESS ? e2 : HUF_ERROR_INVALID_ARGUMENT;
+                base = static_cast<uint8_t *>(p);
+            }
+        }
+        meet.arrive();
+        if (base && size[g]) err[g] = download(c, base + off[g], ps.d_out[0].p, size[g]);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < ndev; g++) th.emplace_back(worker, g);
+    worker(0);
+    for (auto &t : th) t.join();
+    for (int g = 0; g < ndev; g++) {
+        if (err[g] != HUF_ERROR_SUCCESS) return err[g];
+    }
+    if (slab_sizes) {
+        for (int g = 0; g < ndev; g++) slab_sizes[g] = size[g];
+    }
+    return dst->commit ? dst->commit(dst->arg, off[ndev]) : HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_decode_host_multi(huf_b200_ctx_t *const *ctxs, int ndev, const void *h_in,
+                                       uint64_t avail, uint64_t length, const huf_b200_sink_t *dst,
+                                       uint64_t *consumed)
+{
+    using namespace pipe;
+    if (!ctxs || ndev < 1 || ndev > 64 || !dst || !dst->reserve || (!h_in && avail)) return HUF_ERROR_INVALID_ARGUMENT;
+    if (consumed) *consumed = 0;
+    if (!length) return HUF_ERROR_SUCCESS;
+    const uint64_t lim = length < avail ? length : avail;  // blocks start in front of lim
+    struct Part {
+        uint64_t first = ~0ull, end = 0, out = 0;
+        uint64_t hi = 0;         // end of the byte range
+        bool saw_all = false;    // the device held the stream up to its very end
+        huf_error_t err = HUF_ERROR_SUCCESS;
+    };
+    std::vector<Part> part(ndev);
+    std::vector<uint64_t> out_off(ndev + 1, 0);
+    uint8_t *base = nullptr;
+    bool stitched = false;
+    huf_error_t final_err = HUF_ERROR_SUCCESS;
+    int last_dev = -1;       // devices 0..last_dev deliver their slabs
+    uint64_t reached = 0;
+    Rendezvous meet(ndev);
+
+    auto worker = [&](int g) {
+        huf_b200_ctx *c = ctxs[g];
+        Part &me = part[g];
+        // byte range of device g, and the bytes behind it that its last block may need
+        const uint64_t lo = lim / ndev * g, hi = g + 1 == ndev ? lim : lim / ndev * (g + 1);
+        const uint64_t lo16 = lo & ~uint64_t(15);  // the device copy keeps the stream's 16-byte phase
+        uint64_t over = (hi - lo) / 4;
+        if (over < (8ull << 20)) over = 8ull << 20;
+        const uint64_t up_hi = avail - hi < over ? avail : hi + over;
+        me.hi = hi;
+        me.saw_all = up_hi == avail;
+        DeviceGuard guard(c->device);
+        PipeState &ps = c->pipe;
+        huf_error_t e = HUF_ERROR_SUCCESS;
+        if (hi > lo) {
+            e = ps.init();
+            if (e == HUF_ERROR_SUCCESS) e = reserve_device(ps.d_stream, up_hi - lo16 + 64);
+            if (e == HUF_ERROR_SUCCESS) e = upload(c, ps.d_stream.p, static_cast<const uint8_t *>(h_in) + lo16, up_hi - lo16);
+            uint64_t est = 0;
+            if (e == HUF_ERROR_SUCCESS)
+                e = huf_b200_decode_range_plan(c, ps.d_stream.p, up_hi - lo16, lo - lo16, hi - lo16, lo == 0, &est,
+                                               nullptr, HUF_B200_STREAM_PRIVATE);
+            if (e == HUF_ERROR_SUCCESS) e = reserve_device(ps.d_out[0], est + 64);
+            if (e == HUF_ERROR_SUCCESS)
+                e = huf_b200_decode_range_async(c, ps.d_stream.p, up_hi - lo16, lo - lo16, hi - lo16, lo == 0,
+                                                ps.d_out[0].p, ps.d_out[0].cap, HUF_B200_STREAM_PRIVATE);
+            if (e == HUF_ERROR_SUCCESS) {
+                e = huf_b200_decode_range_finish(c, &me.first, &me.end, &me.out);
+                if (me.first != ~0ull) me.first += lo16;
+                me.end += lo16;
+            }
+        }
+        me.err = e;
+        meet.arrive();
+        if (g == 0) {
+            // chain validation across the ranges: every range must begin where the chain of
+            // its predecessors ended; an error of the stream stops the chain there (the output
+            // of the blocks before it is still delivered, like src/decoder.c:218-276 does)
+            uint64_t expect = 0;
+            stitched = true;
+            for (int k = 0; k < ndev; k++) {
+                const Part &p = part[k];
+                out_off[k + 1] = out_off[k];
+                if (k > 0 && expect >= p.hi) continue;  // a block of an earlier range covers this one
+                if (p.first != expect) {
+                    // a header the scan does not recognise, or a false one, at the seam (also:
+                    // device error before any block): the serial lane decides
+                    stitched = false;
+                    break;
+                }
+                last_dev = k;
+                out_off[k + 1] = out_off[k] + p.out;
+                expect = p.end;
+                if (p.err != HUF_ERROR_SUCCESS) {
+                    // (READ_WRITE with bytes left behind the device's copy: the block outgrew the
+                    // overlap, not the stream)
+                    if (p.err == HUF_ERROR_READ_WRITE && !p.saw_all) stitched = false;
+                    final_err = p.err;
+                    break;
+                }
+            }
+            for (int k = last_dev + 1; k < ndev; k++) out_off[k + 1] = out_off[last_dev + 1];
+            reached = expect;
+            if (stitched && final_err == HUF_ERROR_SUCCESS && reached < lim) stitched = false;  // (cannot happen)
+            if (stitched && out_off[last_dev + 1]) {
+                void *p = nullptr;
+                const huf_error_t e2 = dst->reserve(dst->arg, out_off[last_dev + 1], &p);
+                if (e2 != HUF_ERROR_SUCCESS || !p) {
+                    final_err = e2 != HUF_ERROR_SUCCESS ? e2 : HUF_ERROR_INVALID_ARGUMENT;
+                    stitched = false;
+                    last_dev = -2;  // nothing to deliver, no fallback either
+                }
+                base = static_cast<uint8_t *>(p);
+            }
+        }
+        meet.arrive();
+        if (stitched && base && g <= last_dev && me.out) {
+            const huf_error_t e2 = download(c, base + out_off[g], ps.d_out[0].p, me.out);
+            if (e2 != HUF_ERROR_SUCCESS) me.err = e2;
+        }
+    };
+    // (the seam rule needs to know whether device k saw the whole rest of the stream)
+    std::vector<std::thread> th;
+    for (int g = 1; g < ndev; g++) th.emplace_back(worker, g);
+    worker(0);
+    for (auto &t : th) t.join();
+
+    if (debug_on())
+        fprintf(stderr, "huf_b200: decode_host_multi over %d devices: %s, chain reached %llu of %llu\n", ndev,
+                stitched ? "seams validated" : "a seam did not validate: serial lane", (unsigned long long)reached,
+                (unsigned long long)lim);
+    if (debug_on()) {
+        for (int k = 0; k < ndev; k++)
+            fprintf(stderr, "huf_b200:   range %d: ends %llu first %lld chain end %llu out %llu err %d\n", k,
+                    (unsigned long long)part[k].hi, (long long)part[k].first, (unsigned long long)part[k].end,
+                    (unsigned long long)part[k].out, (int)part[k].err);
+    }
+    if (last_dev == -2) return final_err;
+    if (!stitched) {
+        // correctness first: the one-device lane decodes the stream serially span by span
+        huf_b200_source_t src;
+        memset(&src, 0, sizeof(src));
+        src.data = h_in;
+        src.size = avail;
+        return huf_b200_decode_host(ctxs[0], &src, length, dst, consumed);
+    }
+    for (int g = 0; g <= last_dev; g++) {
+        if (part[g].err != HUF_ERROR_SUCCESS && part[g].err != final_err) return part[g].err;
+    }
+    if (consumed) *consumed = reached;
+    if (dst->commit && out_off[last_dev + 1]) {
+        const huf_error_t e2 = dst->commit(dst->arg, out_off[last_dev + 1]);
+        if (e2 != HUF_ERROR_SUCCESS) return e2;
+    }
+    if (final_err == HUF_ERROR_SUCCESS && reached >= avail && reached < length) return HUF_ERROR_READ_WRITE;
+    return final_err;
 }
 
 }  // extern "C"

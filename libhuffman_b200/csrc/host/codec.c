@@ -19,28 +19,80 @@
  * HUF_ERROR_INVALID_ARGUMENT instead of crashing in cleanup.
  */
 #include <pthread.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "internal.h"
 
-/* ---- the process-wide GPU context -------------------------------------------------------- */
+/* ---- the process-wide GPU contexts ------------------------------------------------------- */
+
+/* One context on the current device, created lazily; or one per device listed in the
+ * environment variable HUF_B200_DEVICES ("0,1,2,3" or "all"): huf_encode / huf_decode then split
+ * a large call over those GPUs (contiguous block ranges / byte ranges).  The
+ * reference has no configuration for this (huf_config_t must keep its layout), hence the
+ * environment. */
+#define HUF_MAX_DEVICES 16
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
-static huf_b200_ctx_t *g_ctx;
+static huf_b200_ctx_t *g_ctx[HUF_MAX_DEVICES];
+static int g_nctx;
+
+static huf_error_t
+contexts_create(void)
+{
+    const char *env = getenv("HUF_B200_DEVICES");
+    int want[HUF_MAX_DEVICES];
+    int n = 0;
+
+    if (env && *env) {
+        const int have = huf_b200_device_count();
+        if (!strcmp(env, "all")) {
+            for (int d = 0; d < have && n < HUF_MAX_DEVICES; d++) {
+                want[n++] = d;
+            }
+        } else {
+            const char *p = env;
+            while (*p && n < HUF_MAX_DEVICES) {
+                char *end = NULL;
+                long d = strtol(p, &end, 10);
+                if (end == p) {
+                    break;
+                }
+                if (d >= 0 && d < have) {
+                    want[n++] = (int)d;
+                }
+                p = *end == ',' ? end + 1 : end;
+            }
+        }
+    }
+    if (!n) {
+        want[n++] = -1; /* the current device */
+    }
+    for (int i = 0; i < n; i++) {
+        huf_error_t err = huf_b200_ctx_create(&g_ctx[i], want[i]);
+        if (err != HUF_ERROR_SUCCESS) {
+            while (i-- > 0) {
+                huf_b200_ctx_destroy(&g_ctx[i]);
+            }
+            return err;
+        }
+    }
+    g_nctx = n;
+    return HUF_ERROR_SUCCESS;
+}
 
 huf_error_t
 huf__codec_context(huf_b200_ctx_t **ctx)
 {
     pthread_mutex_lock(&g_lock);
-    if (!g_ctx) {
-        huf_error_t err = huf_b200_ctx_create(&g_ctx, -1);
+    if (!g_nctx) {
+        huf_error_t err = contexts_create();
         if (err != HUF_ERROR_SUCCESS) {
-            g_ctx = NULL;
             pthread_mutex_unlock(&g_lock);
             return err;
         }
     }
-    *ctx = g_ctx;
+    *ctx = g_ctx[0];
     return HUF_ERROR_SUCCESS; /* lock stays held until huf__codec_context_unlock */
 }
 
@@ -48,6 +100,15 @@ void
 huf__codec_context_unlock(void)
 {
     pthread_mutex_unlock(&g_lock);
+}
+
+/* Calls at least this large are split over the listed devices (smaller ones are not worth the
+ * second PCIe link); HUF_B200_MULTI_MIN overrides the threshold in bytes. */
+static uint64_t
+multi_threshold(void)
+{
+    const char *env = getenv("HUF_B200_MULTI_MIN");
+    return env ? (uint64_t)strtoull(env, NULL, 10) : (uint64_t)64 << 20;
 }
 
 /* ---- encoder / decoder objects ----------------------------------------------------------- */
@@ -217,7 +278,15 @@ huf_encode(const huf_config_t *config)
         in_now = src.size;
     }
     make_sink(config->writer, &dst, &ms, huf_b200_encode_bound(in_now, blocksize));
-    huf_error_t err = huf_b200_encode_host(ctx, &src, config->length, blocksize, &dst, &taken);
+    huf_error_t err;
+    if (g_nctx > 1 && src.data && dst.reserve && in_now >= config->length && in_now >= multi_threshold() &&
+        in_now / blocksize >= (uint64_t)g_nctx) {
+        /* whole input at hand, lending sink, enough blocks: one block range per GPU */
+        err = huf_b200_encode_host_multi(g_ctx, g_nctx, src.data, in_now, blocksize, &dst, NULL);
+        taken = err == HUF_ERROR_SUCCESS ? in_now : 0;
+    } else {
+        err = huf_b200_encode_host(ctx, &src, config->length, blocksize, &dst, &taken);
+    }
     huf_memstream_t *m = huf__as_memstream(config->reader);
     if (m) {
         m->rpos += taken;
@@ -250,7 +319,13 @@ huf_decode(const huf_config_t *config)
      * asked for `length` bytes first and for more only if a block needs them. */
     make_source(config->reader, &src);
     make_sink(config->writer, &dst, &ms, config->length + config->length / 2);
-    huf_error_t err = huf_b200_decode_host(ctx, &src, config->length, &dst, &consumed);
+    huf_error_t err;
+    if (g_nctx > 1 && src.data && dst.reserve && src.size >= multi_threshold()) {
+        /* one byte range of the stream per GPU */
+        err = huf_b200_decode_host_multi(g_ctx, g_nctx, src.data, src.size, config->length, &dst, &consumed);
+    } else {
+        err = huf_b200_decode_host(ctx, &src, config->length, &dst, &consumed);
+    }
     huf_memstream_t *m = huf__as_memstream(config->reader);
     if (m) {
         m->rpos += consumed; /* consume exactly the whole blocks, like the unbuffered reference */

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 #define HUF_EMU 1
@@ -129,6 +130,10 @@ inline void fiber_entry()
 // Run one kernel: grid CTAs of `block` threads with `smem` bytes of dynamic shared memory.
 inline void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()> &body)
 {
+    // one kernel at a time: the emulator's CTA state is global, and the multi-device lanes of the
+    // library launch from one host thread per device
+    static std::mutex launch_mu;
+    std::lock_guard<std::mutex> launch_lock(launch_mu);
     for (unsigned b = 0; b < grid; b++) {
         Cta c;
         cta() = &c;

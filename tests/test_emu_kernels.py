@@ -368,3 +368,53 @@ def test_emu_failed_async_leaves_context_usable(emu, harness):
         assert dst.raw[:codec.encode_finish()] == stream
     finally:
         codec.close()
+
+
+def _range_decode_all(lib, stream, cuts, out_cap):
+    """Decode `stream` as byte ranges cut at `cuts` (the multi-GPU decode of SURVEY.md §8(e) on one
+    device): every range decodes the blocks that start in it; returns the stitched bytes after
+    checking that each range begins where its predecessor's chain ended."""
+    codec = DeviceCodec(lib)
+    try:
+        src = C.create_string_buffer(stream, len(stream) + 16)
+        bounds = [0, *cuts, len(stream)]
+        out, expect_first = b"", 0
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            buf = C.create_string_buffer(out_cap + 64)
+            codec.decode_range_async(C.addressof(src), len(stream), lo, hi, C.addressof(buf), out_cap + 64)
+            rc, first, end, n = codec.decode_range_finish()
+            assert rc == 0, (lo, hi, rc)
+            if first is None:
+                assert n == 0 and end == lo   # no block starts in this range (a block spans it)
+                continue
+            assert first == expect_first, (lo, hi, first, expect_first)
+            expect_first = end
+            out += buf.raw[:n]
+        assert expect_first == len(stream)
+        return out
+    finally:
+        codec.close()
+
+
+def test_emu_decode_by_byte_ranges(emu, harness):
+    data = datagen.zipf(12000, 180, seed=14)
+    stream = harness.oracle_encode(data, 2048)          # 6 blocks of ~2 KB
+    n = len(stream)
+    offs = _block_offsets(stream)
+    for cuts in ([n // 2], [1, n // 3, n - 1], [n // 4, n // 4 + 100, n // 4 + 200],
+                 [offs[2], offs[4]]):                   # (the last: cuts exactly on block boundaries)
+        assert _range_decode_all(emu, stream, cuts, len(data)) == data, cuts
+    big = harness.oracle_encode(data[:5000], 0)         # one block: the ranges behind the first are empty
+    assert _range_decode_all(emu, big, [len(big) // 3, len(big) // 2], 5000) == data[:5000]
+
+
+def _block_offsets(stream):
+    """Walk the block chain of a valid stream with the oracle (test helper)."""
+    from oracle import harness as h
+    offs, at = [], 0
+    while at < len(stream):
+        offs.append(at)
+        rc, _, used = h.oracle_decode(stream[at:], 1)
+        assert rc == 0
+        at += used
+    return offs

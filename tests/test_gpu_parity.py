@@ -343,3 +343,182 @@ def test_decode_with_block_index_hint(lib, torch_cuda, codec):
         assert dec.decode_finish() == (0, n, c) and torch.equal(back[:n], x)
     finally:
         dec.close()
+
+
+# ---- round 2: paths the first round never ran on the device --------------------------------------
+
+def test_blocks_above_4mib_and_blocksize_zero(lib, harness):
+    """Blocks above 4 MiB build their code with 64-bit merge keys (k_build<uint64_t>); blocksize 0
+    on a large input -- the reference's C default (src/encoder.c:163-165) -- is one such block."""
+    data = datagen.zipf(48 << 20, 255, seed=11)
+    for bs in (0, 6 << 20):                      # one 48 MiB block; eight 6 MiB blocks
+        want = harness.oracle_encode(data, bs)
+        rc, got = lib.encode(data, bs)
+        assert rc == 0 and got == want, bs
+        rc, back = lib.decode(want)
+        assert rc == 0 and back == data, bs
+    # 4 MiB + a bit with blocksize 0 (the size the round-1 review checked under the emulator)
+    small = data[: (4 << 20) + 70000]
+    rc, got = lib.encode(small, 0)
+    assert rc == 0 and got == harness.oracle_encode(small, 0)
+
+
+def test_more_blocks_than_one_encode_pass(lib, harness):
+    """More than 2^18 blocks: the encoder runs in passes over its workspace, the decoder's sparse
+    header scan overflows its per-chunk slots (dense two-pass scan) and its first candidate
+    workspace (re-sized restart)."""
+    n = (1 << 18) * 6 + 4000 * 6 + 5              # 266 144 blocks of 6 bytes and a short last one
+    data = datagen.zipf(n, 64, seed=12)
+    want = harness.oracle_encode(data, 6)
+    rc, got = lib.encode(data, 6)
+    assert rc == 0 and got == want
+    rc, back = lib.decode(want)
+    assert rc == 0 and back == data
+
+
+def test_general_lane_bit_position_limit(lib):
+    """bit positions inside one block are 32-bit in the general lane.  A block the fast
+    lane declines (foreign tree shape: two-child root) that announces 2^32 symbols is refused with
+    HUF_ERROR_FATAL where the reference would decode it; this test pins where that limit is."""
+    from cases import hdr
+    tree = [300, 65, -1, -1, 66, -1, -1]         # A = 0, B = 1: one bit per symbol
+    payload = bytes(1 << 20)
+    ok = hdr(8 * len(payload), tree) + payload   # 2^23 symbols: fine
+    rc, out = lib.decode(ok)
+    assert rc == 0 and out == b"A" * (8 * len(payload))
+    big = hdr(1 << 32, tree) + bytes(1 << 29)    # 2^32 symbols in 512 MiB of payload
+    rc, out = lib.decode(big)
+    assert rc == 4 and out == b""
+
+
+def test_host_lane_spans_and_streams(lib, harness, monkeypatch, tmp_path):
+    """huf_encode / huf_decode with many spans in flight (stage threads, three CUDA streams), over
+    memory streams, user callbacks and file descriptors."""
+    import os
+    from libhuffman_b200.capi import Config, ReadWriter
+    monkeypatch.setenv("HUF_B200_SPAN_MIB", "4")
+    data = datagen.zipf(70 << 20, 255, seed=13)  # 18 spans of 64 whole blocks
+    want = harness.oracle_encode(data, 65536)
+    rc, got = lib.encode(data, 65536)
+    assert rc == 0 and got == want
+    rc, back = lib.decode(want)
+    assert rc == 0 and back == data
+    # damage in a late span: error code and the output before it are the oracle's
+    bad = bytearray(want)
+    bad[len(bad) * 7 // 8] ^= 0x04
+    rc_o, out_o, _ = harness.oracle_decode(bytes(bad))
+    rc, out = lib.decode(bytes(bad))
+    assert rc == rc_o and (rc != 0 or out == out_o)
+    rc_o, out_o, _ = harness.oracle_decode(want[:-12345])
+    rc, out = lib.decode(want[:-12345])
+    assert (rc, out) == (rc_o, out_o) and rc == 3
+    # file to file through huf_fdopen streams
+    fin, fmid, fout = (str(tmp_path / n) for n in ("in", "mid", "out"))
+    open(fin, "wb").write(data)
+    lib.dll.huf_fdopen.argtypes = [C.POINTER(C.POINTER(ReadWriter)), C.c_int]
+    for a, b, fn, length, blk in ((fin, fmid, "huf_encode", len(data), 65536), (fmid, fout, "huf_decode", len(want), 0)):
+        fa, fb = os.open(a, os.O_RDONLY), os.open(b, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+        ra, rb = C.POINTER(ReadWriter)(), C.POINTER(ReadWriter)()
+        assert lib.dll.huf_fdopen(C.byref(ra), fa) == 0 and lib.dll.huf_fdopen(C.byref(rb), fb) == 0
+        cfg = Config(length=length, blocksize=blk, reader=ra, writer=rb)
+        assert getattr(lib.dll, fn)(C.byref(cfg)) == 0
+        lib.dll.huf_fdclose(C.byref(ra))
+        lib.dll.huf_fdclose(C.byref(rb))
+        os.close(fa)
+        os.close(fb)
+    assert open(fmid, "rb").read() == want and open(fout, "rb").read() == data
+
+
+def test_decode_length_beyond_data(lib, harness):
+    """`length` past the readable bytes used to spin; the reference reports READ_WRITE."""
+    data = datagen.english_text(100000, seed=2)
+    stream = harness.oracle_encode(data, 4096)
+    rc, got = lib.decode(stream, length=len(stream) + 10)
+    assert (rc, got) == (3, data)
+    rc, got = lib.decode(b"", length=10)
+    assert (rc, got) == (3, b"")
+
+
+@pytest.mark.parametrize("shape", ["english", "zipf255", "fibonacci"])
+def test_compiled_reference_agrees_on_medium_inputs(lib, harness, shape):
+    """The authority is the compiled, unmodified reference (oracle/_ref), not its port."""
+    if not harness.reference_available():
+        pytest.skip("oracle/_ref not present")
+    ref = harness.reference()
+    n = 3 << 20
+    data = {"english": lambda: datagen.english_text(n, seed=1), "zipf255": lambda: datagen.zipf(n, 255, seed=2),
+            "fibonacci": lambda: datagen.fibonacci(n, 65536, seed=4)}[shape]()
+    for bs in (65536, 4096):
+        rc, ref_stream = ref.encode(data, bs)
+        assert rc == 0
+        rc, got = lib.encode(data, bs)
+        assert rc == 0 and got == ref_stream, (shape, bs)
+        rc, back = lib.decode(ref_stream)
+        assert rc == 0 and back == data, (shape, bs)
+
+
+def test_decode_by_byte_ranges_on_device(lib, harness, torch_cuda, codec):
+    """The unit of a multi-GPU decode: byte ranges of one stream, each decoding
+    the blocks that start in it, stitched by the host's chain check."""
+    torch = torch_cuda
+    n, bs = 64 << 20, 65536
+    x = datagen.zipf_torch(n, "cuda", 255, seed=21)
+    stream, offs = dev_encode(torch, codec, x, bs)
+    stream = stream.clone()
+    c = stream.numel()
+    st = torch.cuda.current_stream().cuda_stream
+    for cuts in ([c // 2], [c // 8 * k for k in range(1, 8)], [int(offs[100]), int(offs[100]) + 1, c - 5]):
+        bounds = [0, *cuts, c]
+        expect, parts = 0, []
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            est = codec.decode_range_plan(stream.data_ptr(), c, lo, hi, st)
+            out = torch.empty(est + 64, dtype=torch.uint8, device="cuda")
+            codec.decode_range_async(stream.data_ptr(), c, lo, hi, out.data_ptr(), est + 64, st)
+            rc, first, end, m = codec.decode_range_finish()
+            assert rc == 0
+            if first is None:
+                assert m == 0
+                continue
+            assert first == expect
+            expect = end
+            parts.append(out[:m])
+        assert expect == c and torch.equal(torch.cat(parts), x)
+
+
+_TWO_GPU_SCRIPT = r'''
+import sys
+sys.path.insert(0, "{root}")
+import libhuffman_b200
+from libhuffman_b200 import datagen
+from oracle import harness
+harness.build()
+lib = libhuffman_b200.load()
+for n, bs in ((96 << 20, 65536), ((40 << 20) + 777, 1 << 20), (24 << 20, 4096)):
+    data = datagen.zipf(n, 255, seed=31)
+    want = harness.oracle_encode(data, bs)
+    rc, got = lib.encode(data, bs)
+    assert rc == 0 and got == want, ("encode", n, bs)
+    rc, back = lib.decode(want)
+    assert rc == 0 and back == data, ("decode", n, bs)
+    rc_o, out_o, _ = harness.oracle_decode(want[:-999])
+    rc, back = lib.decode(want[:-999])
+    assert (rc, back) == (rc_o, out_o), ("truncated", n, bs)
+print("two-gpu ok")
+'''
+
+
+def test_two_gpus_stitch_parity(lib, torch_cuda):
+    """HUF_B200_DEVICES=0,1: one input split by block range over two GPUs gives the one-GPU
+    (= oracle) stream; one stream split by byte range over two GPUs decodes to the input."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    root = Path(__file__).resolve().parents[1]
+    env = dict(os.environ, HUF_B200_DEVICES="0,1", HUF_B200_MULTI_MIN="0", HUF_B200_DEBUG="1")
+    proc = subprocess.run([sys.executable, "-c", _TWO_GPU_SCRIPT.format(root=root)], env=env,
+                          capture_output=True, text=True, timeout=1200)
+    assert proc.returncode == 0 and "two-gpu ok" in proc.stdout, proc.stdout + proc.stderr
+    assert "seams validated" in proc.stderr

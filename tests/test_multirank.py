@@ -80,3 +80,67 @@ def test_block_ranges_partition():
             assert max(sizes) - min(sizes) <= 1
     assert shard.byte_range(1000, 300, 1, 2) == (600, 1000)
     assert shard.slab_offsets([5, 7, 1]) == [0, 5, 12, 13]
+
+
+_MULTI_DEVICE_SCRIPT = r'''
+import sys
+sys.path.insert(0, "{root}")
+sys.path.insert(0, "{root}/tests")
+sys.path.insert(0, "{root}/tests/emu")
+import numpy as np
+import build_emu
+from cases import foreign_streams
+from libhuffman_b200 import datagen
+from libhuffman_b200.capi import B200Lib
+from oracle import harness
+harness.build()
+lib = B200Lib(build_emu.build())
+rng = np.random.default_rng(5)
+for n, bs in ((11 * 4096 + 123, 4096), (9000, 1000), (30000, 0), (50000, 20000)):
+    data = datagen.zipf(n, 200, seed=3)
+    want = harness.oracle_encode(data, bs)
+    rc, got = lib.encode(data, bs)
+    assert rc == 0 and got == want, ("encode", n, bs)
+    rc, back = lib.decode(want)
+    assert (rc, back) == (0, data), ("decode", n, bs)
+    # `length` in the middle of the stream: whole blocks up to the one that starts before it
+    rc_o, out_o, _ = harness.oracle_decode(want, len(want) // 2)
+    rc, back = lib.decode(want, length=len(want) // 2)
+    assert (rc, back) == (rc_o, out_o), ("length", n, bs)
+    # damaged streams: the error code and the output before the failing block are the oracle's
+    for it in range(6):
+        s = bytearray(want)
+        if it % 3 == 0:
+            s = s[: int(rng.integers(1, len(s)))]
+        elif it % 3 == 1:
+            s[int(rng.integers(0, len(s)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            pos = int(rng.integers(0, max(1, len(s) - 8)))
+            s[pos:pos + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+        s = bytes(s)
+        rc_o, out_o, _ = harness.oracle_decode(s)
+        rc, back = lib.decode(s)
+        assert rc == rc_o and (rc != 0 or back == out_o), ("damaged", n, bs, it, rc, rc_o)
+# headers the scan does not recognise: the seams do not validate, the serial lane takes over
+tail = harness.oracle_encode(datagen.zipf(9000, 100, seed=4), 1500)
+for name, s in foreign_streams():
+    for stream in (s + tail, tail + s + tail):
+        rc_o, out_o, _ = harness.oracle_decode(stream)
+        rc, got = lib.decode(stream)
+        assert (rc, got) == (rc_o, out_o), name
+print("multi-device ok")
+'''
+
+
+def test_several_devices_in_one_call(tmp_path):
+    """HUF_B200_DEVICES: huf_encode splits the block range, huf_decode the byte range of the one
+    stream over the listed devices (three contexts on the emulated device here; the -m gpu lane
+    repeats it on two real GPUs when the box has them).  Results must not depend on the split."""
+    import subprocess
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+    build_emu.build()
+    env = dict(os.environ, HUF_B200_DEVICES="0,0,0", HUF_B200_MULTI_MIN="0")
+    proc = subprocess.run([sys.executable, "-c", _MULTI_DEVICE_SCRIPT.format(root=ROOT)], env=env,
+                          capture_output=True, text=True, timeout=900)
+    assert proc.returncode == 0 and "multi-device ok" in proc.stdout, proc.stdout + proc.stderr
