@@ -52,6 +52,10 @@ enum {
     /* 1: bracket every kernel launch of the following *_async calls with CUDA events on the
      * launching stream; read them with huf_b200_kernel_times after *_finish. */
     HUF_B200_OPT_KERNEL_TIMING = 2,
+    /* 1: launch the instance of the fast decode kernel that does not rely on its lookup table
+     * being 8 KB aligned in the shared window (what the library falls back to by itself when
+     * its probe finds the table elsewhere).  For tests. */
+    HUF_B200_OPT_FORCE_LUT_ADD = 3,
 };
 
 /* Create a context on CUDA device `device` (< 0: the current device).  Fails with

@@ -297,6 +297,10 @@ class DeviceCodec:
         """Candidate blocks of the last decode pass that took the general (slow) lane."""
         return self.lib.dll.huf_b200_last_slow_blocks(self.ctx)
 
+    def set_force_lut_add(self, on: bool) -> None:
+        """Tests: use the fast decode kernel instance that does not need an 8 KB aligned table."""
+        self.lib.check(self.lib.dll.huf_b200_ctx_set_option(self.ctx, 3, int(on)), "set_option")
+
     def set_kernel_timing(self, on: bool) -> None:
         self.lib.check(self.lib.dll.huf_b200_ctx_set_option(self.ctx, 2, int(on)), "set_option")
 

@@ -301,6 +301,17 @@ static_assert(kFastStage % 16 == 0 && kFastRegOff % 16 == 0 && kFastTailOff % 8 
 // The root bit itself is checked separately: a walk on a set root bit is dead.
 __device__ __forceinline__ uint32_t fast_idx(uint32_t win) { return (win >> (32 - kTreeReach - 1)) & (2u * kLutSize - 2u); }
 
+// Shared-window address of the table entry at byte offset `off`.  kLutOr: the table base is 8 KB
+// aligned, so the offset is OR-ed in (one three-input logic instruction forms the address out of
+// the shifted window, the mask and the base); otherwise it is added.  Which one applies depends
+// on where the dynamic shared memory of the kernel starts in the shared window: the host probes
+// that once per context (k_smem_base) and launches the matching instance.
+template <bool kLutOr>
+__device__ __forceinline__ saddr_t lut_at(saddr_t lut_s, uint32_t off)
+{
+    return kLutOr ? saddr_or(lut_s, off) : lut_s + off;
+}
+
 // The three staged words from the one that holds bit `pos` on, kept in registers while a walk
 // moves through its sub-block: every staged word is loaded once per walk (the loads of 32
 // lanes at unrelated positions hit random banks, so each one costs several wavefronts).
@@ -373,6 +384,7 @@ __device__ __forceinline__ uint32_t blind_len(uint32_t e, uint32_t h)
 // Returns the position behind the fourth.  h0..h3 are the four windows: their top bits tell
 // whether a walk started on a set root bit; the entries and the returned position are only
 // meaningful up to the first such walk (it is dead and advances one bit).
+template <bool kLutOr>
 __device__ __forceinline__ uint32_t fast_look4(const BitWin &b, saddr_t lut_s, uint32_t pos,
                                                uint32_t &e0, uint32_t &e1, uint32_t &e2, uint32_t &e3,
                                                uint32_t &h0, uint32_t &h1, uint32_t &h2, uint32_t &h3)
@@ -380,15 +392,15 @@ __device__ __forceinline__ uint32_t fast_look4(const BitWin &b, saddr_t lut_s, u
     const uint32_t w0 = b.w0, w1 = b.w1, w2 = b.w2;
     h0 = __funnelshift_l(w1, w0, pos);                 // stream bits pos .. pos+31
     uint32_t lo = __funnelshift_l(w2, w1, pos);        // stream bits pos+32 .. pos+63
-    e0 = lds_u16(saddr_or(lut_s, fast_idx(h0)));
+    e0 = lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h0)));
     h1 = __funnelshift_l(lo, h0, e0);
     lo = __funnelshift_l(0u, lo, e0);
-    e1 = lds_u16(saddr_or(lut_s, fast_idx(h1)));
+    e1 = lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h1)));
     h2 = __funnelshift_l(lo, h1, e1);
     lo = __funnelshift_l(0u, lo, e1);
-    e2 = lds_u16(saddr_or(lut_s, fast_idx(h2)));
+    e2 = lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h2)));
     h3 = __funnelshift_l(lo, h2, e2);
-    e3 = lds_u16(saddr_or(lut_s, fast_idx(h3)));
+    e3 = lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h3)));
     // lengths sit in bits [3:0], bits [5:4] are clear in every kind of entry: no carries
     return pos + ((e0 + e1 + e2 + e3) & 0x3fu);
 }
@@ -399,13 +411,14 @@ __device__ __forceinline__ uint32_t fast_look4(const BitWin &b, saddr_t lut_s, u
 // deterministic rule serves a speculative start -- this one re-synchronises quickly on skewed
 // codes -- and a dead step on the proven trajectory sends the block to the general lane.
 constexpr uint64_t kStepOk = 1ull << 63;
+template <bool kLutOr>
 __device__ __noinline__ uint64_t fast_step(saddr_t sw_s, saddr_t lut_s, const FastTail *ft, uint32_t n,
                                            uint32_t pos)
 {
     uint32_t w0, w1;
     lds_u32x2(sw_s + ((pos >> 5) << 2), w0, w1);
     const uint32_t win = __funnelshift_l(bswap32(w1), bswap32(w0), pos);
-    const uint32_t e = lds_u16(saddr_or(lut_s, fast_idx(win)));
+    const uint32_t e = lds_u16(lut_at<kLutOr>(lut_s, fast_idx(win)));
     const uint32_t root = win >> 31;
     if (!((e & kFastFlags) | root)) {
         return kStepOk | ((uint64_t)(e >> 8) << 32) | (pos + (e & 0xfu));
@@ -504,13 +517,9 @@ __device__ unsigned long long g_fast_prof[16];
 #define HUF_PROF_CNT(k)
 #endif
 
-__global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
+template <bool kLutOr>
+__device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
 {
-#ifdef HUF_EMU
-    uint8_t *dyn = hufemu::dyn_smem();
-#else
-    extern __shared__ __align__(16) uint8_t dyn[];
-#endif
     FastSmall &sm = *reinterpret_cast<FastSmall *>(dyn + kFastSmallOff);
     FastTail &ft = *reinterpret_cast<FastTail *>(dyn + kFastTailOff);
     const int tid = threadIdx.x;
@@ -530,7 +539,9 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
     uint64_t tma_base = 0;     // ... from this stream offset
     if (tid == 0) mbar_init(&sm.mbar, 1);
 #ifndef HUF_EMU
-    if (lut_s & (uint32_t)(kFastLutAlign - 1)) __trap();  // the table base is OR-ed into its index
+    // (the host launches this instance only after probing the shared window; a mismatch is a
+    // loud failure, never a silent mis-decode)
+    if (kLutOr && (lut_s & (uint32_t)(kFastLutAlign - 1))) __trap();
 #endif
     const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
@@ -757,21 +768,21 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     // (mask = all ones under a set root bit, computed beside the table load)
                     const uint32_t h0 = __funnelshift_l(b.w1, b.w0, p);
                     uint32_t lo = __funnelshift_l(b.w2, b.w1, p);
-                    const uint32_t l0 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h0))), h0);
+                    const uint32_t l0 = blind_len(lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h0))), h0);
                     const uint32_t h1 = __funnelshift_l(lo, h0, l0);
                     lo = __funnelshift_l(0u, lo, l0);
-                    const uint32_t l1 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h1))), h1);
+                    const uint32_t l1 = blind_len(lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h1))), h1);
                     const uint32_t h2 = __funnelshift_l(lo, h1, l1);
                     lo = __funnelshift_l(0u, lo, l1);
-                    const uint32_t l2 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h2))), h2);
+                    const uint32_t l2 = blind_len(lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h2))), h2);
                     const uint32_t h3 = __funnelshift_l(lo, h2, l2);
-                    const uint32_t l3 = blind_len(lds_u16(saddr_or(lut_s, fast_idx(h3))), h3);
+                    const uint32_t l3 = blind_len(lds_u16(lut_at<kLutOr>(lut_s, fast_idx(h3))), h3);
                     const uint32_t np = p + ((l0 + l1 + l2 + l3) & 0x3fu);
                     if (HAS_LONG && ((l0 | l1 | l2 | l3) & 0x80u)) {
                         // a code word longer than the table reach among the four: this group is
                         // walked with exact steps (a blind single-bit step would leave the
                         // trajectory of the exact walk and cost a repair round later)
-                        for (int k = 0; k < 4 && p < limit; k++) p = (uint32_t)fast_step(sw_s, lut_s, &ft, sm.nlong, p);
+                        for (int k = 0; k < 4 && p < limit; k++) p = (uint32_t)fast_step<kLutOr>(sw_s, lut_s, &ft, sm.nlong, p);
                         if (p >= limit) return p;
                         win_load(b, sw_s, p);
                         continue;
@@ -836,7 +847,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                     if (pos < my_hi) win_load(b, sw_s, pos);
                     while (pos < my_hi) {
                         uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
-                        const uint32_t np = fast_look4(b, lut_s, pos, e0, e1, e2, e3, h0, h1, h2, h3);
+                        const uint32_t np = fast_look4<kLutOr>(b, lut_s, pos, e0, e1, e2, e3, h0, h1, h2, h3);
                         if (!(((e0 | e1 | e2 | e3) & kFastFlags) | ((h0 | h1 | h2 | h3) >> 31))) {
                             // four plain table hits
                             const uint32_t lo2 = __byte_perm(e0, e1, 0x0051);
@@ -876,7 +887,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                         // irregular (special entry or dead root among the four): one exact step
                         {
                             const uint32_t at = pos;
-                            const uint64_t r = fast_step(sw_s, lut_s, &ft, sm.nlong, pos);
+                            const uint64_t r = fast_step<kLutOr>(sw_s, lut_s, &ft, sm.nlong, pos);
                             pos = (uint32_t)r;
                             if (r & kStepOk) {
                                 put((uint32_t)(r >> 32) & 0xffu);
@@ -999,14 +1010,14 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
                         BitWin b;
                         win_load(b, sw_s, p);
                         uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
-                        const uint32_t np = fast_look4(b, lut_s, p, e0, e1, e2, e3, h0, h1, h2, h3);
+                        const uint32_t np = fast_look4<kLutOr>(b, lut_s, p, e0, e1, e2, e3, h0, h1, h2, h3);
                         if (!(((e0 | e1 | e2 | e3) & kFastFlags) | ((h0 | h1 | h2 | h3) >> 31))) {
                             p = np;
                             q += 4;
                             continue;
                         }
                     }
-                    const uint64_t r = fast_step(sw_s, lut_s, &ft, sm.nlong, p);
+                    const uint64_t r = fast_step<kLutOr>(sw_s, lut_s, &ft, sm.nlong, p);
                     p = (uint32_t)r;
                     if (r & kStepOk) q++; else dead = 1;
                 }
@@ -1084,6 +1095,36 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
         for (int k = 0; k < 12; k++) atomicAdd(&g_fast_prof[k], pacc[k]);
     }
 #endif
+}
+
+#ifdef HUF_EMU
+#define HUF_DYN_SMEM(name) uint8_t *name = hufemu::dyn_smem()
+#else
+#define HUF_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#endif
+
+// The instance every launch uses today: dynamic shared memory starts at shared-window address
+// 0x400 (no static shared memory, 1 KB reserved by the system), which puts the table at 0x4000.
+__global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
+{
+    HUF_DYN_SMEM(dyn);
+    decode_fast_body<true>(a, dyn);
+}
+
+// Same kernel with the table offset ADDED to its base: launched when the probe finds the table
+// at an address that is not 8 KB aligned (a driver or toolkit that reserves a different amount
+// of shared memory), one more integer instruction per code word.
+__global__ void __launch_bounds__(kFT, 4) k_decode_unaligned(DecArgs a)
+{
+    HUF_DYN_SMEM(dyn);
+    decode_fast_body<false>(a, dyn);
+}
+
+// Where does dynamic shared memory of a kernel without static shared memory start?
+__global__ void k_smem_base(uint32_t *out)
+{
+    HUF_DYN_SMEM(dyn);
+    if (threadIdx.x == 0) out[0] = (uint32_t)smem_addr(dyn);
 }
 
 }  // namespace hufb200

@@ -131,6 +131,8 @@ struct huf_b200_ctx {
     uint32_t dec_stage = 0;         // dynamic smem bytes for k_decode_slow
     bool slow_ready = false;        // k_decode_slow attribute set
     bool fast_ready = false;        // k_decode attributes set
+    bool lut_or = true;             // k_decode's table is 8 KB aligned in the shared window (probed)
+    bool force_lut_add = false;     // HUF_B200_OPT_FORCE_LUT_ADD: always launch k_decode_unaligned
     int fast_per_sm = 1;
     uint64_t dec_stage_want = 80 * 1024;  // payload bytes of one block staged in shared memory
 
@@ -316,6 +318,10 @@ huf_error_t huf_b200_ctx_set_option(huf_b200_ctx_t *ctx, int option, int64_t val
         return HUF_ERROR_SUCCESS;
     case HUF_B200_OPT_KERNEL_TIMING:
         ctx->timing = value != 0;
+        return HUF_ERROR_SUCCESS;
+    case HUF_B200_OPT_FORCE_LUT_ADD:
+        ctx->force_lut_add = value != 0;
+        ctx->fast_ready = false;  // choose the kernel instance again
         return HUF_ERROR_SUCCESS;
     default:
         return HUF_ERROR_INVALID_ARGUMENT;
@@ -593,6 +599,22 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
                                                              c->dec_stage));
         if (per_sm < 1) per_sm = 1;
         if (!c->fast_ready) {
+            // is the lookup table of k_decode 8 KB aligned in the shared window?  (It is when
+            // dynamic shared memory starts at 0x400; ask the device instead of assuming.)
+            if (!c->force_lut_add) {
+                CTX_LAUNCH(c, k_smem_base, 1, 32, 1024, st, reinterpret_cast<uint32_t *>(c->d_result + 15));
+                uint64_t base = 0;
+                CU_TRY(cudaMemcpyAsync(&base, c->d_result + 15, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaStreamSynchronize(st));
+                c->lut_or = (((uint32_t)base + (uint32_t)kFastLutOff) & (uint32_t)(kFastLutAlign - 1)) == 0;
+#ifdef HUF_EMU
+                c->lut_or = true;  // (addresses are host pointers there; both instances add)
+#endif
+            } else {
+                c->lut_or = false;
+            }
+            CU_TRY(cudaFuncSetAttribute(k_decode_unaligned, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kFastDyn));
             CU_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kFastDyn));
             int fper = 1;
@@ -604,7 +626,10 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         // fast lane: tree walk (one lane per candidate), chunked region decode; whatever it
         // declines goes through the general lane
         CTX_LAUNCH(c, k_tree, c->sm_count * 6, 32, kTreeDyn, st, a);
-        CTX_LAUNCH(c, k_decode, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
+        if (c->lut_or)
+            CTX_LAUNCH(c, k_decode, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
+        else
+            CTX_LAUNCH(c, k_decode_unaligned, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
         CTX_LAUNCH(c, k_decode_slow, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
         CTX_LAUNCH(c, k_verify, 1, kScanThreads, 0, st, a);
     }

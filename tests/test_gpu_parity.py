@@ -526,3 +526,29 @@ def test_two_gpus_stitch_parity(lib, torch_cuda):
                           capture_output=True, text=True, timeout=1200)
     assert proc.returncode == 0 and "two-gpu ok" in proc.stdout, proc.stdout + proc.stderr
     assert "seams validated" in proc.stderr
+
+
+def test_fast_lane_without_table_alignment(lib, harness, torch_cuda):
+    """k_decode ORs the table index into an 8 KB aligned base; where dynamic shared memory starts
+    is probed per context, and k_decode_unaligned (ADD) is what runs if the table lands elsewhere.
+    Force that instance: same bytes, still the fast lane."""
+    torch = torch_cuda
+    dec = DeviceCodec(lib, 0)
+    dec.set_force_lut_add(True)
+    try:
+        for name, data in (("zipf255", datagen.zipf(8 << 20, 255, seed=2)),
+                           ("fibonacci", datagen.fibonacci(4 << 20, 65536, seed=4)),
+                           ("geometric", datagen.geometric(4 << 20, seed=4))):
+            stream = harness.oracle_encode(data, 65536)
+            s_t = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
+            rc, back, used = dev_decode(torch, dec, s_t, len(data))
+            assert rc == 0 and used == len(stream), name
+            assert back.cpu().numpy().tobytes() == data, name
+            assert dec.slow_blocks() == 0, name
+            names = None
+        dec.set_kernel_timing(True)
+        rc, back, used = dev_decode(torch, dec, s_t, len(data))
+        names = [k for k, _ in dec.kernel_times()]
+        assert "k_decode_unaligned" in names and "k_decode" not in names
+    finally:
+        dec.close()
