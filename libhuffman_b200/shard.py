@@ -1,9 +1,21 @@
-"""Multi-GPU sharding of the block codec: contiguous block ranges, no data-path collective.
+"""Multi-GPU sharding of the block codec, one process per GPU.
 
-Blocks are self-contained (reference src/encoder.c:345,360-373 resets all state per block), so
-GPU g of G encodes blocks [g*B/G, (g+1)*B/G) into its own slab and the host concatenates the
-slabs in rank order; slab g starts at the exclusive scan of the slab sizes.  Only sizes are
-exchanged (a few bytes per rank, host side)."""
+Encode: blocks are self-contained (reference src/encoder.c:345,360-373 resets all state per
+block), so rank r of N encodes the contiguous block range [r*B/N, (r+1)*B/N) into its own slab;
+the ONE stream is the slabs in rank order, slab r starting at the exclusive scan of the slab
+sizes.  Only the sizes are exchanged.
+
+Decode: the stream has no block index (src/decoder.c:218-276 finds block k+1 by decoding block
+k), so rank r takes the BYTE range [r*C/N, (r+1)*C/N) of the one stream plus an overlap for its
+last block, finds the headers in it, decodes the blocks that start in it
+(huf_b200_decode_range_async) and reports (first block offset, chain end, decoded bytes).  The
+chain is validated across ranks on the host: range r must begin where the chain of the ranges
+before it ended.  Decoded slabs concatenate in rank order.
+
+No data-path collective: `torch.distributed` carries sizes, tuples and -- once, to lay the one
+stream out by byte range the way a reader of a file would find it -- the few MiB around every
+cut that live on the neighbouring rank.
+"""
 from __future__ import annotations
 
 
@@ -31,3 +43,34 @@ def slab_offsets(slab_sizes: list[int]) -> list[int]:
         run += s
     out.append(run)
     return out
+
+
+def stream_cuts(total: int, world: int) -> list[int]:
+    """Byte ranges of the one stream for decode: rank r scans [cuts[r], cuts[r+1])."""
+    return [total // world * r for r in range(world)] + [total]
+
+
+def range_pieces(offs: list[int], lo: int, hi: int) -> list[tuple[int, int, int]]:
+    """Which slab bytes make up stream bytes [lo, hi): (rank, from, to) in slab-local offsets."""
+    out = []
+    for r in range(len(offs) - 1):
+        a, b = max(lo, offs[r]), min(hi, offs[r + 1])
+        if a < b:
+            out.append((r, a - offs[r], b - offs[r]))
+    return out
+
+
+def validate_chain(parts: list[tuple[int | None, int, int]], cuts: list[int]) -> tuple[bool, int, list[int]]:
+    """Host-side chain check over per-rank (first block offset or None, chain end, decoded bytes),
+    all in stream offsets.  Returns (ok, end of the chain, exclusive scan of the decoded sizes).
+    A range that lies entirely inside a block of an earlier range contributes nothing."""
+    expect, outs = 0, [0]
+    for r, (first, end, n) in enumerate(parts):
+        if r > 0 and expect >= cuts[r + 1]:
+            outs.append(outs[-1])
+            continue
+        if first != expect:
+            return False, expect, outs
+        expect = end
+        outs.append(outs[-1] + n)
+    return expect == cuts[-1], expect, outs

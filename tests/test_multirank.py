@@ -56,6 +56,68 @@ def _worker(rank: int, world: int, port: int, tmp: str):
     Path(tmp, f"ok{rank}").write_text("ok")
 
 
+def _sharded_worker(rank: int, world: int, port: int, tmp: str):
+    """The one-process-per-GPU driver (libhuffman_b200/sharded.py) on CPU tensors: block ranges
+    in, one stream out, the stream laid out by byte range, range decode, chain check."""
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import build_emu
+    from libhuffman_b200 import datagen, shard
+    from libhuffman_b200.capi import B200Lib
+    from libhuffman_b200.sharded import ShardedCodec
+    from oracle import harness
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    emu = B200Lib(build_emu.build())
+    sc = ShardedCodec(emu, rank, world, torch.device("cpu"))
+    for bs, n in ((2048, 23 * 2048 + 77), (4096, 6 * 4096)):
+        data = datagen.zipf(n, 150, seed=9)
+        whole = harness.oracle_encode(data, bs)
+        lo, hi = shard.byte_range(n, bs, rank, world)
+        x = torch.frombuffer(bytearray(data[lo:hi]), dtype=torch.uint8)
+        comp = torch.empty(sc.enc.encode_bound(hi - lo, bs), dtype=torch.uint8)
+        sc.encode_async(x, bs, comp)
+        size = sc.encode_finish()
+        sizes = [r[0] for r in sc.all_gather_ints([size])]
+        offs = shard.slab_offsets(sizes)
+        assert offs[-1] == len(whole)
+        assert comp[:size].numpy().tobytes() == whole[offs[rank]:offs[rank + 1]]
+        # the one stream by byte range: a small overlap on purpose (a block is ~2-4 KB here)
+        buf, base, cuts = sc.redistribute(comp, sizes, overlap=6000)
+        want_lo, want_hi = cuts[rank] & ~15, min(len(whole), cuts[rank + 1] + 6000)
+        assert base == want_lo and buf.numpy().tobytes() == whole[want_lo:want_hi]
+        est = sc.decode_plan(buf, base, cuts)
+        out = torch.empty(est + 64, dtype=torch.uint8)
+        sc.decode_async(buf, base, cuts, out)
+        mine = sc.decode_finish(base)
+        ok, end, outs = sc.validate(mine, cuts)
+        assert ok and end == len(whole) and outs[-1] == n, (ok, end, outs)
+        assert out[:mine[3]].numpy().tobytes() == data[outs[rank]:outs[rank + 1]]
+    sc.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    Path(tmp, f"sharded{rank}").write_text("ok")
+
+
+def test_two_rank_sharded_codec(tmp_path):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+    from oracle import harness
+    build_emu.build()
+    harness.build()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "sharded0").exists() and (tmp_path / "sharded1").exists()
+
+
 def test_two_rank_block_range_sharding(tmp_path):
     import torch.multiprocessing as mp
 
