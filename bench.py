@@ -10,7 +10,10 @@ streams, host buffers, host<->device copies inside the timed region).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 Under torchrun (N > 1) every rank codes its own 1 GiB shard (contiguous block ranges of an
-N GiB input; blocks are independent, so there is no data-path collective): weak scaling.
+N GiB input; blocks are independent, so there is no data-path collective): weak scaling, that
+is `value`.  The same line carries, as extra keys: `strong` (BASELINE configs[3]: ONE 64 GiB job
+over the N GPUs, stitched stream, sharded decode, `stitched_ok`), and at N = 1 `sweep` (configs
+2-4: shapes and block sizes) and `config5_python_streaming` (configs[4]).
 """
 from __future__ import annotations
 
@@ -47,6 +50,12 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-mib", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the shape/block-size sweep and the config-5 leg (N=1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the one-job-over-N-GPUs leg")
+    ap.add_argument("--sweep-mib", type=int, default=512)
+    ap.add_argument("--config5-mib", type=int, default=4096)
+    ap.add_argument("--strong-gib", type=int, default=64)
+    ap.add_argument("--strong-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -214,17 +223,336 @@ def run_reference_arm(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 
+NOMINAL_HBM_GBS = 8000.0   # north_star's nominal peak (SURVEY.md §8d asks for both fractions)
+
+
+def _device_timer(torch, dist, world, dev):
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, fin):
+        """Device time of `steps` back-to-back invocations, max over ranks, in seconds."""
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        fin()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+        barrier()
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return barrier, timed
+
+
+def _shape_tensor(torch, datagen, name, n, dev, bs):
+    """The named shapes of BASELINE.json configs 2-3 in HBM (host-generated ones are tiled)."""
+    if name in ("zipf255", "zipf256"):
+        return datagen.zipf_torch(n, dev, 255 if name == "zipf255" else 256, seed=2)
+    if name == "uniform":
+        return datagen.uniform_torch(n, dev, 256, seed=3)
+    small = min(n, 64 << 20)
+    gen = {"fibonacci": lambda: datagen.fibonacci(small, bs if bs <= (1 << 20) else 65536, seed=4),
+           "geometric": lambda: datagen.geometric(small, seed=4),
+           "english": lambda: datagen.english_text(small, seed=1)}[name]
+    t = torch.frombuffer(bytearray(gen()), dtype=torch.uint8).to(dev)
+    return t.repeat((n + small - 1) // small)[:n].contiguous()
+
+
+def sweep_leg(torch, lib, dev, peak, mib):
+    """Configs 2-4 on one GPU, device resident: every named shape at 64 KiB blocks, the Zipf
+    block-size sweep 4 KiB ... 1 MiB, the 256-symbol variants through the opt-in decoder mode."""
+    from libhuffman_b200 import datagen
+    from libhuffman_b200.capi import DeviceCodec
+    n = mib << 20
+    enc = DeviceCodec(lib, dev.index)
+    dec = DeviceCodec(lib, dev.index, accept_1025=True)
+    st = torch.cuda.current_stream().cuda_stream
+    cases = [("zipf255", bs) for bs in (4096, 16384, 262144, 1 << 20)]
+    cases += [(name, 65536) for name in ("zipf256", "uniform", "fibonacci", "geometric", "english")]
+    cases.append(("fibonacci", 1 << 20))
+    rows = []
+    for name, bs in cases:
+        x = _shape_tensor(torch, datagen, name, n, dev, bs)
+        cap = enc.encode_bound(n, bs)
+        comp = torch.empty(cap, dtype=torch.uint8, device=dev)
+        back = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+
+        def e():
+            enc.encode_async(x.data_ptr(), n, bs, comp.data_ptr(), cap, st)
+
+        e()
+        csize = enc.encode_finish()
+
+        def d():
+            dec.decode_async(comp.data_ptr(), csize, csize, back.data_ptr(), n + 64, st)
+
+        d()
+        ok = dec.decode_finish() == (0, n, csize) and bool(torch.equal(back[:n], x))
+
+        def timed(fn, fin, reps=5):
+            for _ in range(2):
+                fn()
+                fin()
+            torch.cuda.synchronize()
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(reps):
+                fn()
+            t1.record()
+            torch.cuda.synchronize()
+            fin()
+            return t0.elapsed_time(t1) / reps / 1e3
+
+        te, td = timed(e, enc.encode_finish), timed(d, dec.decode_finish)
+        rows.append({"shape": name, "blocksize": bs, "mib": mib, "ratio": round(csize / n, 4), "roundtrip_ok": ok,
+                     "encode_gbs": round(n / te / GB, 1), "decode_gbs": round(n / td / GB, 1),
+                     "encode_frac": round((n + csize) / te / GB / peak, 4),
+                     "decode_frac": round((n + csize) / td / GB / peak, 4)})
+        del x, comp, back
+    enc.close()
+    dec.close()
+    return rows
+
+
+def config5_leg(mib: int):
+    """BASELINE configs[4]: the reference's HuffmanCompressor (unchanged cffi package, built against
+    this library by scripts/build_reference_suites.py) streaming `mib` MiB in 64 MiB chunks."""
+    pkg = ROOT / "oracle" / "_ref_suites" / "huffmanfile_gpu"
+    if not (pkg / "huffmanfile").is_dir():
+        return {"unavailable": "oracle/_ref_suites not built (needs the reference checkout at build time)"}
+    code = f"""
+import sys, time
+sys.path.insert(0, "."); sys.path.insert(0, {str(ROOT)!r})
+import huffmanfile
+from libhuffman_b200 import datagen
+chunk = 64 << 20
+data = datagen.zipf(chunk, 255, seed=5)
+c = huffmanfile.HuffmanCompressor()
+c.compress(data)                      # warm-up: context, arenas, pinned buffers
+t0 = time.perf_counter(); n = 0
+for _ in range({mib} // 64):
+    n += len(c.compress(data))
+n += len(c.flush())
+dt = time.perf_counter() - t0
+d = huffmanfile.HuffmanDecompressor()
+one = huffmanfile.compress(data)
+t1 = time.perf_counter(); back = d.decompress(one); dt2 = time.perf_counter() - t1
+assert back == data
+print("RESULT", {mib} << 20, n, dt, chunk / dt2)
+"""
+    try:
+        proc = subprocess.run([sys.executable, "-c", code], cwd=pkg, capture_output=True, text=True, timeout=900)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "timed out"}
+    rows = [ln for ln in proc.stdout.splitlines() if ln.startswith("RESULT")]
+    if proc.returncode != 0 or not rows:
+        return {"unavailable": (proc.stderr or proc.stdout)[-300:]}
+    _, total, out, dt, dec_bps = rows[0].split()
+    return {"workload": f"HuffmanCompressor.compress()+flush(), {mib} MiB Zipf(1.1)/255 in 64 MiB chunks, default blocksize 131072",
+            "compress_gbs": int(total) / float(dt) / GB, "decompress_gbs": float(dec_bps) / GB,
+            "ratio": int(out) / int(total), "api": "reference huffmanfile package (cffi) on libhuffman_b200.so"}
+
+
+def strong_leg(args, torch, dist, lib, dev, rank, world, peak):
+    """BASELINE configs[3]: ONE job sharded over the GPUs (libhuffman_b200/sharded.py): the input is
+    partitioned by contiguous block ranges, every GPU encodes its range, the slabs form one
+    stream (exclusive scan of their sizes); that stream is split by BYTE range for decode, every
+    GPU finds and decodes the blocks that start in its range, the host validates the chain.
+    Strong scaling: the total is fixed as N grows (N = 1 runs the first half as a sample: the
+    whole job with input, stream and output resident does not fit one GPU)."""
+    from libhuffman_b200 import datagen, shard
+    from libhuffman_b200.sharded import ShardedCodec
+    barrier, timed = _device_timer(torch, dist, world, dev)
+    bs = args.blocksize
+    total = args.strong_gib << 30
+    job = total if world > 1 else total // 2
+    nb = job // bs
+    chunk = 64 << 20                                      # generator granule: seed = chunk index
+    b_lo, b_hi = shard.block_range(nb, rank, world)
+    lo, hi = b_lo * bs, b_hi * bs
+    n = hi - lo
+    x = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def gen(into, at_lo, at_hi):
+        """bytes [at_lo, at_hi) of the job: chunk c holds zipf_torch(chunk, seed=1000+c)."""
+        c0 = at_lo // chunk
+        while c0 * chunk < at_hi:
+            piece = datagen.zipf_torch(chunk, dev, args.nsym, seed=1000 + c0)
+            a, b = max(at_lo, c0 * chunk), min(at_hi, (c0 + 1) * chunk)
+            into[a - at_lo:b - at_lo] = piece[a - c0 * chunk:b - c0 * chunk]
+            c0 += 1
+
+    gen(x, lo, hi)
+    sc = ShardedCodec(lib, rank, world, dev, dev.index, accept_1025=args.nsym > 255)
+    st = torch.cuda.current_stream().cuda_stream
+    cap = sc.enc.encode_bound(n, bs)
+    comp = torch.empty(cap, dtype=torch.uint8, device=dev)
+
+    def enc_step():
+        sc.encode_async(x, bs, comp, st)
+
+    enc_step()
+    size = sc.encode_finish()
+    sizes = [r[0] for r in sc.all_gather_ints([size])]
+    offs = shard.slab_offsets(sizes)
+    csize = offs[-1]
+    # position-dependent checksum of the one stream (equal across N <=> same stitched bytes)
+    s1 = s2 = 0
+    step = 256 << 20
+    for at in range(0, size, step):
+        v = comp[at:min(size, at + step)].to(torch.int64)
+        pos = (torch.arange(v.numel(), device=dev, dtype=torch.int64) + (offs[rank] + at)) % 65521 + 1
+        s1 += int(v.sum().item())
+        s2 += int((v * pos).sum().item()) % (1 << 61)
+        del v, pos
+    sums = sc.all_gather_ints([s1, s2 % (1 << 61), b_hi * bs])
+    half = job // 2 if world > 1 else job
+    first_half = [sum(r[0] for r in sums if r[2] <= half), sum(r[1] for r in sums if r[2] <= half) % (1 << 61)]
+    t_enc = timed(enc_step, args.strong_steps, sc.encode_finish)
+    del x   # (the check below regenerates what it needs; the stream laid out by byte range needs the room)
+
+    # ---- the one stream by byte range (setup, timed separately), then the sharded decode
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    overlap = max(8 << 20, 4 * bs)
+    buf, base, cuts = sc.redistribute(comp, sizes, overlap)
+    torch.cuda.synchronize()
+    t_layout = time.perf_counter() - t0
+    moved = buf.numel() - max(0, min(cuts[rank + 1] + overlap, offs[rank + 1]) - max(base, offs[rank]))
+    if world > 1:
+        del comp   # (at N = 1 the buffer is a view of it)
+        comp = None
+    est = sc.decode_plan(buf, base, cuts, st)
+    back = torch.empty(est + 64, dtype=torch.uint8, device=dev)
+
+    def dec_step():
+        sc.decode_async(buf, base, cuts, back, st)
+
+    dec_step()
+    mine = sc.decode_finish(base)
+    ok, end, outs = sc.validate(mine, cuts)
+    stitched_ok = bool(ok and end == csize and outs and outs[-1] == job)
+    if stitched_ok:
+        # my decoded slab is the job's bytes [outs[rank], outs[rank+1]): regenerate and compare
+        want = torch.empty(outs[rank + 1] - outs[rank], dtype=torch.uint8, device=dev)
+        gen(want, outs[rank], outs[rank + 1])
+        stitched_ok = bool(torch.equal(back[:mine[3]], want))
+        del want
+    flags = sc.all_gather_ints([int(stitched_ok)])
+    stitched_ok = all(f[0] for f in flags)
+    t_dec = timed(dec_step, args.strong_steps, lambda: sc.decode_finish(base))
+    moved_all = sum(r[0] for r in sc.all_gather_ints([int(moved)]))
+    sc.close()
+    del comp, back, buf
+    torch.cuda.empty_cache()
+    return {
+        "scaling": "strong",
+        "workload": f"{args.strong_gib} GiB Zipf(1.1)/{args.nsym} in {bs} B blocks as ONE job over the GPUs"
+                    + ("" if world > 1 else f" (N=1: the first {job >> 30} GiB as a sample, the rest does not fit beside it)"),
+        "job_bytes": job, "stream_bytes": csize, "n_gpus": world,
+        "encode_gbs": job * args.strong_steps / t_enc / GB,
+        "decode_gbs": job * args.strong_steps / t_dec / GB,
+        "value": 2 * job * args.strong_steps / (t_enc + t_dec) / GB,
+        "encode_frac_of_n_peaks": (job + csize) * args.strong_steps / t_enc / GB / (peak * world),
+        "decode_frac_of_n_peaks": (job + csize) * args.strong_steps / t_dec / GB / (peak * world),
+        "stitched_ok": stitched_ok,
+        "stream_checksum": [csize, sum(r[0] for r in sums), sum(r[1] for r in sums) % (1 << 61)],
+        "first_half_checksum": first_half,
+        "layout_by_byte_range_ms": 1e3 * t_layout, "bytes_moved_between_gpus": moved_all,
+        "decode_split": "byte ranges of the one stream + 8 MiB overlap, header scan per range, host chain check",
+        "collectives_in_timed_region": "none (sizes and (first, end, n) tuples only, outside it)",
+    }
+
+
+def e2e_leg(args, torch, dist, lib, dev, world, host: bytes, csize: int, barrier):
+    """The same round trip through the reference-facing C API with HOST buffers: huf_encode then
+    huf_decode over huf_memopen streams; host<->device copies are inside the timed region.  Two
+    protocols: streams opened once and rewound per step (steady state, what a streaming caller
+    like the Python compressor does) and streams opened fresh for every step (first call: the
+    output pages have never been touched)."""
+    from libhuffman_b200.capi import Config
+    n = len(host)
+    bs = args.blocksize
+    cap = lib.dll.huf_b200_encode_bound(n, bs)
+
+    def one(src, mid, dst, check):
+        barrier()
+        t0 = time.perf_counter()
+        cfg = Config(length=n, blocksize=bs, reader=src.rw, writer=mid.rw)
+        rc = lib.dll.huf_encode(C.byref(cfg))
+        assert rc == 0, rc
+        clen = len(mid)
+        cfg = Config(length=clen, reader=mid.rw, writer=dst.rw)
+        rc = lib.dll.huf_decode(C.byref(cfg))
+        assert rc == 0, rc
+        dt = time.perf_counter() - t0
+        assert clen == csize and len(dst) == n
+        if check:   # (untimed) the decoded bytes, not just their count
+            assert C.string_at(dst.buf, n) == host, "e2e round trip differs from the input"
+        return dt
+
+    def reduce_max(t):
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # steady state: one set of streams, rewound (input re-written untimed) every step
+    src, mid, dst = lib.memstream(n), lib.memstream(cap), lib.memstream(n)
+    t_reuse = 0.0
+    for it in range(-1, args.e2e_steps):
+        for s_ in (src, mid, dst):
+            lib.dll.huf_memrewind(s_.rw)
+        src.write(host)
+        dt = one(src, mid, dst, check=it < 0)
+        if it >= 0:
+            t_reuse += dt
+    for s_ in (src, mid, dst):
+        s_.close()
+    # first call: fresh streams every step
+    t_fresh = 0.0
+    for it in range(args.e2e_steps):
+        src, mid, dst = lib.memstream(n), lib.memstream(cap), lib.memstream(n)
+        src.write(host)
+        t_fresh += one(src, mid, dst, check=False)
+        for s_ in (src, mid, dst):
+            s_.close()
+    t_reuse, t_fresh = reduce_max(t_reuse), reduce_max(t_fresh)
+    return {"value": 2 * n * world * args.e2e_steps / t_reuse / GB, "unit": "GB/s",
+            "h2d_bytes_per_step": n + csize, "d2h_bytes_per_step": csize + n,
+            "protocol": "huf_memopen streams opened once, rewound and refilled (untimed) per step",
+            "fresh_streams_value": 2 * n * world * args.e2e_steps / t_fresh / GB,
+            "fresh_streams_protocol": "three new huf_memopen streams per step: output pages are first-touched inside the timed region",
+            "api": "huf_encode + huf_decode over huf_memopen streams (pageable host buffers; spans of 32 MiB pipelined "
+                   "through pinned buffers: host copy, H2D, kernels, D2H, host copy overlap)",
+            "copy_threads": os.environ.get("HUF_B200_COPY_THREADS", "cores - 2")}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and "HUF_B200_COPY_THREADS" not in os.environ:
+        # the ranks of one box share its cores: the copy pool of every rank gets its share
+        os.environ["HUF_B200_COPY_THREADS"] = str(max(2, (os.cpu_count() or 8) // world))
 
     import libhuffman_b200
     from libhuffman_b200 import datagen
     from libhuffman_b200.capi import DeviceCodec
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -242,12 +570,7 @@ def run_b200_arm(args):
     comp = torch.empty(cap, dtype=torch.uint8, device=dev)
     back = torch.empty(n + 64, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier, timed = _device_timer(torch, dist, world, dev)
 
     # one checked round trip: sizes, parity of the data path used below
     enc_ctx.encode_async(x.data_ptr(), n, bs, comp.data_ptr(), cap, stream)
@@ -272,23 +595,6 @@ def run_b200_arm(args):
         assert enc_ctx.encode_finish() == csize
         r = dec_ctx.decode_finish()
         assert r == (0, n, csize), r
-
-    def timed(fn, steps, fin):
-        """Device time of `steps` back-to-back invocations, max over ranks, in seconds."""
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        fin()
-        t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
-        barrier()
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     for _ in range(max(3, args.warmup)):
         both()
@@ -326,69 +632,50 @@ def run_b200_arm(args):
         ctx.set_kernel_timing(False)
     kavg = {k: sum(v) / len(v) for k, v in kt.items()}
 
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+
     # end to end through the C API with host buffers (memory streams)
     e2e = None
-    h2d = d2h = 0
     if args.e2e_steps > 0:
-        from libhuffman_b200.capi import Config
         host = x.cpu().numpy().tobytes()
-        t_e2e = 0.0
-        clen = 0
-        for it in range(-1, args.e2e_steps):   # it == -1: one untimed warm-up (context, arenas, pinned buffers)
-            # untimed: put the step's input into a host memory stream, as a caller would have it
-            src = lib.memstream(n)
-            src.write(host)
-            mid = lib.memstream(cap)
-            dst = lib.memstream(n)
-            barrier()
-            t0 = time.perf_counter()
-            cfg = Config(length=n, blocksize=bs, reader=src.rw, writer=mid.rw)
-            rc = lib.dll.huf_encode(C.byref(cfg))
-            assert rc == 0, rc
-            clen = len(mid)
-            cfg = Config(length=clen, reader=mid.rw, writer=dst.rw)
-            rc = lib.dll.huf_decode(C.byref(cfg))
-            assert rc == 0, rc
-            torch.cuda.synchronize()
-            if it >= 0:
-                t_e2e += time.perf_counter() - t0
-            ok = len(dst) == n
-            if ok and it < 0:
-                # (untimed) the decoded bytes, not just their count: memcmp against the input
-                ok = C.string_at(dst.buf, n) == host
-            for s_ in (src, mid, dst):
-                s_.close()
-            assert ok, "e2e round trip through huf_encode/huf_decode differs from the input"
+        e2e = e2e_leg(args, torch, dist, lib, dev, world, host, csize, barrier)
         del host
-        assert clen == csize
-        tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-        barrier()
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
-        e2e = 2 * n * world * args.e2e_steps / t_e2e / GB
-        h2d = n + csize
-        d2h = csize + n
+    enc_ctx.close()
+    dec_ctx.close()
+    del x, comp, back
+    torch.cuda.empty_cache()
+
+    # extra legs: the other configs of BASELINE.json, each a driver-visible key of the same line
+    extra = {}
+    if world == 1 and not args.no_extra:
+        extra["sweep"] = sweep_leg(torch, lib, dev, peak, args.sweep_mib)
+        extra["config5_python_streaming"] = config5_leg(args.config5_mib)
+    strong = None
+    if not args.no_strong:
+        strong = strong_leg(args, torch, dist, lib, dev, rank, world, peak)
 
     if rank == 0:
-        peaks = {}
-        pk = ROOT / "MEASURED_PEAKS.json"
-        if pk.exists():
-            peaks = json.loads(pk.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
         # dominant kernel of the step and its algorithmic bytes: N + C either way
         dom = max(kavg, key=kavg.get) if kavg else None
         algo = float(n + csize)
         roof = None
         if dom:
             achieved = algo / (kavg[dom] / 1e3) / GB
+            enc_gbs_algo = (n + csize) * args.steps / t_enc / GB
+            dec_gbs_algo = (n + csize) * args.steps / t_dec / GB
             roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": measured_traffic(dom), "peak_source": peak_src,
+                    "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": achieved / NOMINAL_HBM_GBS,
                     "algorithmic_bytes_per_launch": algo,
                     "kernel_ms": {k: round(v, 4) for k, v in sorted(kavg.items())},
-                    "encode_path_frac": (n + csize) * args.steps / t_enc / GB / peak,
-                    "decode_path_frac": (n + csize) * args.steps / t_dec / GB / peak}
+                    "encode_path_frac": enc_gbs_algo / peak / world, "decode_path_frac": dec_gbs_algo / peak / world,
+                    "encode_path_frac_nominal": enc_gbs_algo / NOMINAL_HBM_GBS / world,
+                    "decode_path_frac_nominal": dec_gbs_algo / NOMINAL_HBM_GBS / world}
         line = {
             "metric": METRIC,
             "value": 2 * n * world * args.steps / t_rt / GB,
@@ -412,10 +699,11 @@ def run_b200_arm(args):
             "decode_with_block_index_gbs": n * world * args.steps / t_dech / GB,
             "roofline": roof,
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "huf_encode + huf_decode over huf_memopen streams (pageable host buffers, pinned bounce buffers inside the library)"},
+            "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
+            "strong": strong,
         }
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:
             mib = args.cpu_sample_mib
             kind, total, per_round = cpu_reference_run(1, mib, args.nsym, bs, 1)
@@ -425,8 +713,6 @@ def run_b200_arm(args):
                                     "encode_gbs": total / e / GB, "decode_gbs": total / d / GB}
         print(json.dumps(line), flush=True)
 
-    enc_ctx.close()
-    dec_ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

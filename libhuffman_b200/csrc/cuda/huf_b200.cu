@@ -381,7 +381,9 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
                                   void *stream)
 {
     if (!c || (!d_in && length) || (!d_out && length)) return HUF_ERROR_INVALID_ARGUMENT;
-    if (c->dec_pending || c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    // (an encode may be enqueued again while one is pending -- several on one stream, one finish
+    // for the last -- but not while a decode of this context is in flight)
+    if (c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
     // the call is pending (encode_finish owed) only once everything was enqueued: a failure on
     // the way (workspace allocation, launch error) leaves the context free for the next call
     const huf_error_t e = encode_enqueue(c, d_in, length, blocksize, d_out, out_capacity, stream);
@@ -650,7 +652,7 @@ huf_error_t decode_start(huf_b200_ctx_t *c, const void *d_in, uint64_t avail, ui
                          void *stream)
 {
     if (!c || (!d_in && avail) || (!d_out && out_capacity)) return HUF_ERROR_INVALID_ARGUMENT;
-    if (c->enc_pending || c->dec_pending) return HUF_ERROR_INVALID_ARGUMENT;
+    if (c->enc_pending) return HUF_ERROR_INVALID_ARGUMENT;
     DeviceGuard g(c->device);
     if (!g.ok) return HUF_ERROR_FATAL;
     c->cur = pick_stream(c, stream);

@@ -58,18 +58,30 @@ class ShardedCodec:
         if self.world == 1:
             return slab[: sizes[0]], 0, cuts
         import torch.distributed as dist
+        # what I hold of everybody's range; my own share is copied locally, not through the exchange
         in_splits, send = [], []
         for d in range(self.world):
             a, b = max(want[d][0], offs[self.rank]), min(want[d][1], offs[self.rank + 1])
-            n = max(0, b - a)
+            n = max(0, b - a) if d != self.rank else 0
             in_splits.append(n)
             if n:
                 send.append(slab[a - offs[self.rank]: b - offs[self.rank]])
         inp = torch.cat(send) if send else torch.empty(0, dtype=torch.uint8, device=self.device)
-        out_splits = [max(0, min(hi, offs[s + 1]) - max(lo, offs[s])) for s in range(self.world)]
-        buf = torch.empty(sum(out_splits) + 64, dtype=torch.uint8, device=self.device)
-        dist.all_to_all_single(buf[: sum(out_splits)], inp, out_splits, in_splits)
-        return buf[: sum(out_splits)], lo, cuts
+        pieces = [max(0, min(hi, offs[s + 1]) - max(lo, offs[s])) for s in range(self.world)]
+        out_splits = [p if s != self.rank else 0 for s, p in enumerate(pieces)]
+        got = torch.empty(sum(out_splits), dtype=torch.uint8, device=self.device)
+        dist.all_to_all_single(got, inp, out_splits, in_splits)
+        buf = torch.empty(sum(pieces) + 64, dtype=torch.uint8, device=self.device)
+        at = src = 0
+        for s, p in enumerate(pieces):
+            if s == self.rank:
+                a = max(lo, offs[s]) - offs[s]
+                buf[at:at + p] = slab[a:a + p]
+            else:
+                buf[at:at + p] = got[src:src + p]
+                src += p
+            at += p
+        return buf[: sum(pieces)], lo, cuts
 
     # ---- decode: the blocks that start in my byte range ----------------------------------------------
 
