@@ -124,6 +124,8 @@ struct huf_b200_ctx {
     bool dec_pending = false;
     uint64_t dec_first = 0;         // offset the pending decode call started at
     uint64_t dec_first_cand = ~0ull;  // offset of the first block the call found (range mode)
+    uint32_t *dec_terms = nullptr;    // terminal slots of very large decode calls (sized after the scan)
+    uint64_t dec_terms_cap = 0;
     DecArgs dec{};
     bool dec_dense = false;         // stream has many tiny blocks: use the exact two-pass header scan
     const uint64_t *hint_off = nullptr;  // optional block index for the next decode (device pointer)
@@ -299,6 +301,7 @@ huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx)
         c->pipe.release();
         if (c->enc_ws.base) cudaFree(c->enc_ws.base);
         if (c->dec_ws.base) cudaFree(c->dec_ws.base);
+        if (c->dec_terms) cudaFree(c->dec_terms);
         if (c->d_status) cudaFree(c->d_status);
         if (c->d_result) cudaFree(c->d_result);
         if (c->h_result) cudaFreeHost(c->h_result);
@@ -542,8 +545,12 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     need += Arena::padded((a.nchunks + 1) * sizeof(uint64_t));
     need += 4 * Arena::padded((max_cand + 1) * sizeof(uint64_t));
     need += 3 * Arena::padded(max_cand * sizeof(uint32_t));
-    // terminal slots of the fast lane: enough for every block of ~1 KiB and larger
-    uint64_t term_slots = span / 1024 + 4096;
+    // Terminal slots of the fast lane (3.2 KB per candidate).  Ordinary calls get enough for every
+    // block of ~1 KiB and larger up front, so the whole pass is enqueued without a host round
+    // trip.  Above 2 GiB of stream that guess would reserve tens of GB: such calls learn the
+    // candidate count first (one synchronisation, negligible at that size) and reserve exactly.
+    const bool exact_terms = !plan_only && span > (2ull << 30);
+    uint64_t term_slots = plan_only || exact_terms ? 0 : span / 1024 + 4096;
     if (term_slots > max_cand) term_slots = max_cand;
     need += Arena::padded(term_slots * kTermStride * sizeof(uint32_t));
     if (!c->dec_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
@@ -578,6 +585,24 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     }
     CTX_LAUNCH(c, k_gather, c->sm_count * 4, 256, 0, st, a);
     CTX_LAUNCH(c, k_scan_olen, 1, kScanThreads, 0, st, a);
+    if (exact_terms) {
+        uint64_t found = 0;
+        CU_TRY(cudaMemcpyAsync(&found, c->d_result, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        const uint64_t want = (found + 16) * kTermStride * sizeof(uint32_t);
+        if (want > c->dec_terms_cap) {
+            if (c->dec_terms) cudaFree(c->dec_terms);
+            c->dec_terms = nullptr;
+            c->dec_terms_cap = 0;
+            if (cudaMalloc(&c->dec_terms, want + want / 8) != cudaSuccess) {
+                cudaGetLastError();
+                return HUF_ERROR_MEMORY_ALLOCATION;
+            }
+            c->dec_terms_cap = want + want / 8;
+        }
+        a.terms = c->dec_terms;
+        a.term_slots = found + 16;
+    }
     if (!plan_only) {
         // dynamic shared memory: payload staging for one block (adapts to the stream's block size)
         uint64_t want = c->dec_stage_want;
