@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
     const bool vec_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 
     const uint64_t in_aligned = a.avail & ~uint64_t(15);  // bytes readable with 16-byte loads
+    // the 16-byte group that holds a proven start (none: an offset no group has)
+    const uint64_t proven16 = a.first_proven && a.first < lim ? find_base(a.first) : ~uint64_t(0);
     for (uint32_t it0 = 0; it0 < kFindChunk / 512; it0 += 4) {
         if (c0 + (uint64_t)it0 * 512 >= lim) break;  // warp-uniform: nothing left in this chunk
         // four independent 16-byte loads in flight per lane; lane 0 also fetches the 16 bytes
@@ -205,8 +207,7 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
                         mask |= 1u << i;
                 }
             }
-            // a proven start is always block 0
-            if (a.first_proven && a.first >= o0 && a.first < o0 + 16 && a.first < lim) mask |= 1u << (uint32_t)(a.first - o0);
+            if (o0 == proven16) mask |= 1u << (uint32_t)(a.first & 15);  // a proven start is always block 0
         }
         const uint32_t n = __popc(mask);
         total += n;
