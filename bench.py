@@ -676,9 +676,10 @@ def run_b200_arm(args):
                     "peak_nominal": NOMINAL_HBM_GBS, "frac_nominal": achieved / NOMINAL_HBM_GBS,
                     "algorithmic_bytes_per_launch": algo,
                     "kernel_ms": {k: round(v, 4) for k, v in sorted(kavg.items())},
-                    "encode_path_frac": enc_gbs_algo / peak / world, "decode_path_frac": dec_gbs_algo / peak / world,
-                    "encode_path_frac_nominal": enc_gbs_algo / NOMINAL_HBM_GBS / world,
-                    "decode_path_frac_nominal": dec_gbs_algo / NOMINAL_HBM_GBS / world}
+                    # (per GPU: n and csize are one rank's bytes, the time is the slowest rank's)
+                    "encode_path_frac": enc_gbs_algo / peak, "decode_path_frac": dec_gbs_algo / peak,
+                    "encode_path_frac_nominal": enc_gbs_algo / NOMINAL_HBM_GBS,
+                    "decode_path_frac_nominal": dec_gbs_algo / NOMINAL_HBM_GBS}
         line = {
             "metric": METRIC,
             "value": 2 * n * world * args.steps / t_rt / GB,

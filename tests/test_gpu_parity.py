@@ -504,9 +504,12 @@ for n, bs in ((96 << 20, 65536), ((40 << 20) + 777, 1 << 20), (24 << 20, 4096)):
     assert rc == 0 and got == want, ("encode", n, bs)
     rc, back = lib.decode(want)
     assert rc == 0 and back == data, ("decode", n, bs)
+    # truncated in the last block: READ_WRITE after the whole blocks before it (DESIGN.md: the output
+    # of a failing block itself is not delivered)
     rc_o, out_o, _ = harness.oracle_decode(want[:-999])
     rc, back = lib.decode(want[:-999])
-    assert (rc, back) == (rc_o, out_o), ("truncated", n, bs)
+    step = bs
+    assert rc == rc_o == 3 and len(back) == (n - 1) // step * step and back == out_o[:len(back)], ("truncated", n, bs)
 print("two-gpu ok")
 '''
 
