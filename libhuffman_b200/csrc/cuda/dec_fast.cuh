@@ -363,6 +363,65 @@ __device__ __forceinline__ void win_advance(BitWin &b, saddr_t sw_s, uint32_t po
 #endif
 }
 
+// The window moves on by `adv` (0, 1 or 2) words; `at` is the shared address of its new first
+// word.  Branch-free: predicated register moves and predicated loads of the one or two new words.
+__device__ __forceinline__ void win_step(BitWin &b, saddr_t at, uint32_t adv)
+{
+#ifdef HUF_EMU
+    if (adv == 1) {
+        b.w0 = b.w1;
+        b.w1 = b.w2;
+        b.w2 = bswap32(lds_u32(at + 8));
+    } else if (adv == 2) {
+        b.w0 = b.w2;
+        b.w1 = bswap32(lds_u32(at + 4));
+        b.w2 = bswap32(lds_u32(at + 8));
+    }
+#else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p1, p2;\n\t"
+        "setp.ne.u32 p1, %4, 0;\n\t"
+        "setp.gt.u32 p2, %4, 1;\n\t"
+        "@p1 mov.u32 %0, %1;\n\t"
+        "@p1 mov.u32 %1, %2;\n\t"
+        "@p2 mov.u32 %0, %2;\n\t"
+        "@p2 ld.shared.u32 %1, [%3+4];\n\t"
+        "@p1 ld.shared.u32 %2, [%3+8];\n\t"
+        "@p2 prmt.b32 %1, %1, 0, 0x0123;\n\t"
+        "@p1 prmt.b32 %2, %2, 0, 0x0123;\n\t"
+        "}"
+        : "+r"(b.w0), "+r"(b.w1), "+r"(b.w2)
+        : "r"(at), "r"(adv));
+#endif
+}
+
+// a * b + c on the multiply-add pipe (the compiler would pick the integer ALU's shift-add)
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+#ifdef HUF_EMU
+    return a * b + c;
+#else
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#endif
+}
+
+// Table offset for the bulk walk.  The walk is bound by the integer ALU pipe (shifts, logic,
+// compares: one warp instruction every other cycle) while the multiply-add pipe idles, so the
+// right shift by 18 is done as the high half of a multiplication by 2^14; the factor comes
+// from the kernel arguments because a literal would be turned back into a shift.
+__device__ __forceinline__ uint32_t bulk_idx(uint32_t win, uint32_t mul14)
+{
+#if defined(HUF_EMU) || defined(HUF_NO_MULHI_IDX)
+    (void)mul14;
+    return fast_idx(win);
+#else
+    return __umulhi(win, mul14) & (2u * kLutSize - 2u);
+#endif
+}
+
 // Length field for the blind walk: the entry, or 1 when the window starts on a set root bit
 // (two instructions: arithmetic shift + one three-input logic op).
 __device__ __forceinline__ uint32_t blind_len(uint32_t e, uint32_t h)
@@ -544,6 +603,7 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
     if (kLutOr && (lut_s & (uint32_t)(kFastLutAlign - 1))) __trap();
 #endif
     const bool in_ok = (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
+    const uint32_t mul14 = a.mul14;  // 1 << (32 - 18), see bulk_idx
 
     for (;;) {
         // blocks are handed out dynamically (result[11] is the work counter): block costs differ
@@ -844,6 +904,55 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
                         sh = 32 - 8 * npend;
                     };
                     BitWin b;
+#ifndef HUF_NO_BULK_WALK
+                    // Bulk phase: groups of four look-ups that lie inside my sub-block whatever
+                    // they decode to (a group consumes at most 4 x 13 bits), with the checks
+                    // for special entries and set root bits deferred to the end of the phase:
+                    // the entries and windows of all groups are OR-ed together, and if anything
+                    // irregular shows up the phase is thrown away and the careful loop below
+                    // decodes the sub-block from its start (so what is kept is exactly what that
+                    // loop would have produced).  Per group this saves the check, a branch pair
+                    // and the pending-byte bookkeeping; the third look-up takes its window from
+                    // the group's first 64 bits with the summed lengths (<= 26 bits), which saves
+                    // two funnel shifts.  Blocks with long-code records never qualify.
+                    if (!sm.nlong && pos + 4u * (uint32_t)kTreeReach <= my_hi) {
+                        const uint32_t bulk_last = my_hi - 4u * (uint32_t)kTreeReach;  // last start of a group
+                        uint32_t p = pos, fe = 0, fh = 0;
+                        uint32_t pw = p >> 5;   // staged word that holds bit p (w0 of the window)
+                        saddr_t wq = wp;
+                        win_load(b, sw_s, p);
+                        do {
+                            const uint32_t h0 = __funnelshift_l(b.w1, b.w0, p);
+                            const uint32_t lo = __funnelshift_l(b.w2, b.w1, p);
+                            const uint32_t e0 = lds_u16(lut_at<kLutOr>(lut_s, bulk_idx(h0, mul14)));
+                            const uint32_t h1 = __funnelshift_l(lo, h0, e0);
+                            const uint32_t e1 = lds_u16(lut_at<kLutOr>(lut_s, bulk_idx(h1, mul14)));
+                            const uint32_t s2 = e0 + e1;                 // low five bits: l0 + l1 <= 26
+                            const uint32_t h2 = __funnelshift_l(lo, h0, s2);
+                            const uint32_t lo2 = __funnelshift_l(0u, lo, s2);
+                            const uint32_t e2 = lds_u16(lut_at<kLutOr>(lut_s, bulk_idx(h2, mul14)));
+                            const uint32_t h3 = __funnelshift_l(lo2, h2, e2);
+                            const uint32_t e3 = lds_u16(lut_at<kLutOr>(lut_s, bulk_idx(h3, mul14)));
+                            const uint32_t np = p + ((s2 + e2 + e3) & 0x3fu);
+                            fe |= e0 | e1 | e2 | e3;
+                            fh |= h0 | h1 | h2 | h3;
+                            const uint32_t lo2s = __byte_perm(e0, e1, 0x0051);
+                            const uint32_t hi2s = __byte_perm(e2, e3, 0x0051);
+                            sts_u32(wq, __byte_perm(lo2s, hi2s, 0x5410));
+                            wq = min(wq + (saddr_t)kRegRow, wp_end);
+                            // window advance by 0, 1 or 2 words (the word index travels with the
+                            // loop, the address is a multiply-add: both off the integer ALU pipe)
+                            const uint32_t nw = np >> 5;
+                            win_step(b, mad_u32(nw, 4u, sw_s), nw - pw);
+                            pw = nw;
+                            p = np;
+                        } while (p <= bulk_last);
+                        if (!((fe & kFastFlags) | (fh >> 31))) {
+                            pos = p;   // all plain table hits: keep them
+                            wp = wq;
+                        }
+                    }
+#endif
                     if (pos < my_hi) win_load(b, sw_s, pos);
                     while (pos < my_hi) {
                         uint32_t e0, e1, e2, e3, h0, h1, h2, h3;

@@ -52,6 +52,7 @@ struct DecArgs {
     uint32_t accept_1025;
     uint32_t count_only; // plan mode: do not write output
     uint32_t stage_cap;  // bytes of dynamic shared memory usable as output staging
+    uint32_t mul14;      // 1 << 14, as a run-time value (dec_fast.cuh bulk_idx)
     // workspace
     uint32_t *chunk_cnt;   // [nchunks]
     uint32_t *slots;       // [nchunks][kFindSlots] chunk-relative candidate offsets (sparse mode)

@@ -528,6 +528,7 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
     a.out_base = out_base;
     a.accept_1025 = (uint32_t)c->accept_1025;
     a.count_only = plan_only ? 1u : 0u;
+    a.mul14 = 1u << 14;
 
     const uint64_t lim = a.length < a.avail ? a.length : a.avail;
     const uint64_t span = lim > first ? lim - first : 0;
