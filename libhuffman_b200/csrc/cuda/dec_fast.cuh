@@ -583,7 +583,7 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
     FastTail &ft = *reinterpret_cast<FastTail *>(dyn + kFastTailOff);
     const int tid = threadIdx.x;
 #ifdef HUF_PHASE_PROF
-    unsigned long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long pt = clock64();
 #endif
     const uint64_t ncand = a.result[0];
@@ -950,9 +950,13 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
                         if (!((fe & kFastFlags) | (fh >> 31))) {
                             pos = p;   // all plain table hits: keep them
                             wp = wq;
+                            HUF_PROF_CNT(12);
+                        } else {
+                            HUF_PROF_CNT(13);
                         }
                     }
 #endif
+                    HUF_PROF_CNT(14);
                     if (pos < my_hi) win_load(b, sw_s, pos);
                     while (pos < my_hi) {
                         uint32_t e0, e1, e2, e3, h0, h1, h2, h3;
@@ -1201,7 +1205,7 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
     }
 #ifdef HUF_PHASE_PROF
     if (tid == 0) {
-        for (int k = 0; k < 12; k++) atomicAdd(&g_fast_prof[k], pacc[k]);
+        for (int k = 0; k < 16; k++) atomicAdd(&g_fast_prof[k], pacc[k]);
     }
 #endif
 }

@@ -55,3 +55,4 @@ for k, nm in enumerate(names):
     print(f"  {nm:24s} {100.0 * v[k] / tot:6.2f} %   {v[k] / max(v[7], 1):9.0f} cycles per chunk")
 print(f"  chunks {v[7]}  blocks {v[9]}  repair rounds {v[8]}  chunks/block {v[7] / max(v[9], 1):.2f}  rounds/chunk {v[8] / max(v[7], 1):.3f}")
 print(f"  cycles per chunk (thread 0 timeline) {tot / max(v[7], 1):.0f}")
+print(f"  thread 0 walks {v[14]}: bulk phase kept {v[12]}, thrown away {v[13]}")
