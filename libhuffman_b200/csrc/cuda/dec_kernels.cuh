@@ -126,6 +126,47 @@ __device__ __forceinline__ bool header_plausible(const DecArgs &a, uint64_t off)
 // host reruns with the exact two-pass scheme (MODE 0 + MODE 1).
 constexpr uint32_t kFindSlots = 8;
 
+// Borrow-trick prefilter over the 16 offsets of one lane: bytes o+9 .. o+26 are the words d2, d3
+// (the lane's own bytes 8..15) and n0, n1, n2 (bytes 16..27, the next lane's first twelve).  A
+// zero byte in z marks an offset whose byte o+11 is 0x01 (high byte of tree[0] = 255 + n) and
+// whose byte o+9 is below 8 (high byte of tree_len <= 0x04); the subtraction flags every zero
+// byte (and, harmlessly, sometimes the byte above one).  1 in 8000 random offsets survives.
+__device__ __forceinline__ uint32_t find_prefilter(uint32_t d2, uint32_t d3, uint32_t n0, uint32_t n1, uint32_t n2)
+{
+    const uint32_t d[5] = {d2, d3, n0, n1, n2};
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t w11 = __funnelshift_r(d[j], d[j + 1], 24);
+        const uint32_t w9 = __funnelshift_r(d[j], d[j + 1], 8);
+        const uint32_t z = (w11 ^ 0x01010101u) | (w9 & 0xf8f8f8f8u);
+        any |= (z - 0x01010101u) & ~z;
+    }
+    return any & 0x80808080u;
+}
+
+// Exact candidate mask of a lane whose prefilter fired: the per-offset byte tests, then the full
+// signature of every survivor.
+__device__ __forceinline__ uint32_t find_exact(const DecArgs &a, uint64_t o0, uint64_t lim, uint32_t d2, uint32_t d3,
+                                               uint32_t n0, uint32_t n1, uint32_t n2)
+{
+    const uint32_t d[5] = {d2, d3, n0, n1, n2};
+    uint32_t pre = 0, mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t w11 = __funnelshift_r(d[j], d[j + 1], 24);
+        const uint32_t w9 = __funnelshift_r(d[j], d[j + 1], 8);
+        const uint32_t eq = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
+        pre |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * j);
+    }
+    while (pre) {
+        const int i = __ffs(pre) - 1;
+        pre &= pre - 1;
+        if (o0 + i >= a.first && o0 + i < lim && header_plausible(a, o0 + i)) mask |= 1u << i;
+    }
+    return mask;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
 {
@@ -144,76 +185,13 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
     const uint64_t in_aligned = a.avail & ~uint64_t(15);  // bytes readable with 16-byte loads
     // the 16-byte group that holds a proven start (none: an offset no group has)
     const uint64_t proven16 = a.first_proven && a.first < lim ? find_base(a.first) : ~uint64_t(0);
-    for (uint32_t it0 = 0; it0 < kFindChunk / 512; it0 += 4) {
-        if (c0 + (uint64_t)it0 * 512 >= lim) break;  // warp-uniform: nothing left in this chunk
-        // four independent 16-byte loads in flight per lane; lane 0 also fetches the 16 bytes
-        // behind the fourth row (what lane 31 needs to look past its own bytes there)
-        uint4 v[5];
-#pragma unroll
-        for (int u = 0; u < 5; u++) {
-            const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;
-            v[u] = make_uint4(0, 0, 0, 0);
-            if ((u < 4 || lane == 0) && vec_ok && (c0 & 15) == 0 && o0 + 16 <= in_aligned)
-                v[u] = ld_stream_u4(a.in + o0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-        const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;  // offsets o0 .. o0+15
-        uint32_t mask = 0;                                               // bit i: o0+i is a candidate
-        // the 16 bytes that follow come from the next lane; lane 31's are lane 0's of the next
-        // row (already in registers): lane 0 offers that row to the rotating shuffle
-        const int nl = (lane + 1) & 31;
-        const uint32_t n0 = __shfl_sync(kFull, lane == 0 ? v[u + 1].x : v[u].x, nl);
-        const uint32_t n1 = __shfl_sync(kFull, lane == 0 ? v[u + 1].y : v[u].y, nl);
-        const uint32_t n2 = __shfl_sync(kFull, lane == 0 ? v[u + 1].z : v[u].z, nl);
-        const bool fast = vec_ok && (c0 & 15) == 0 && o0 + 32 <= in_aligned;
-        if (o0 < lim) {
-            // bytes o0+11 .. o0+26 decide the pre-filter
-            if (fast) {
-                const uint32_t d[8] = {v[u].x, v[u].y, v[u].z, v[u].w, n0, n1, n2, 0u};
-                // tree[0] high byte (offsets 11+4j .. 14+4j) must be 0x01 and the tree_len high
-                // byte (offsets 9+4j .. 12+4j) at most 0x04: 1 in 13000 random offsets, so the
-                // per-offset bit mask is only assembled when some byte lane survived
-                // Cheap test first: z has a zero byte wherever byte o+11 is 0x01 and byte o+9 is
-                // below 8; the borrow trick flags every such byte (and, harmlessly, sometimes
-                // the byte above one).  The exact per-offset masks are only built for a lane
-                // that the cheap test did not clear.
-                uint32_t any = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t w11 = __funnelshift_r(d[2 + j], d[3 + j], 24);
-                    const uint32_t w9 = __funnelshift_r(d[2 + j], d[3 + j], 8);
-                    const uint32_t z = (w11 ^ 0x01010101u) | (w9 & 0xf8f8f8f8u);
-                    any |= (z - 0x01010101u) & ~z;
-                }
-                uint32_t pre = 0;
-                if (any & 0x80808080u) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t w11 = __funnelshift_r(d[2 + j], d[3 + j], 24);
-                        const uint32_t w9 = __funnelshift_r(d[2 + j], d[3 + j], 8);
-                        const uint32_t eq = __vcmpeq4(w11, 0x01010101u) & __vcmpleu4(w9, 0x04040404u);
-                        pre |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * j);
-                    }
-                }
-                while (pre) {
-                    const int i = __ffs(pre) - 1;
-                    pre &= pre - 1;
-                    if (o0 + i >= a.first && o0 + i < lim && header_plausible(a, o0 + i)) mask |= 1u << i;
-                }
-            } else {
-                for (int i = 0; i < 16; i++) {
-                    const uint64_t o = o0 + i;
-                    if (o >= a.first && o < lim && o + 12 <= a.avail && a.in[o + 11] == 1 && header_plausible(a, o))
-                        mask |= 1u << i;
-                }
-            }
-            if (o0 == proven16) mask |= 1u << (uint32_t)(a.first & 15);  // a proven start is always block 0
-        }
+    const int nl = (lane + 1) & 31;
+
+    // ordered emit of one row's candidates: lanes in order, offsets in order inside a lane
+    auto emit = [&](uint32_t mask, uint64_t o0) {
         const uint32_t n = __popc(mask);
         total += n;
         if (EMIT && __any_sync(kFull, mask != 0)) {
-            // ordered emit: lanes in order, offsets in order inside a lane
             const uint32_t incl = warp_incl_scan(n);
             uint64_t at = wr + incl - n;
             uint32_t m = mask;
@@ -229,7 +207,69 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
             }
             wr += __shfl_sync(kFull, incl, 31);
         }
-        }  // u
+    };
+
+    // Interior chunk: every offset of it lies behind `first` and in front of `lim`, the bytes its
+    // last lane looks ahead into are readable with vector loads, and no proven start sits in it.
+    // Nothing has to be tested per row then: the loop streams 512 bytes per row through the
+    // prefilter (the row behind is in flight while one is tested) and only a row with a survivor
+    // -- one in 16 of a compressed payload -- builds exact masks.
+    const uint64_t lim_lean = lim < in_aligned ? lim : in_aligned;
+    if (vec_ok && c0 >= a.first && c0 + kFindChunk + 544 <= lim_lean && (proven16 < c0 || proven16 >= c0 + kFindChunk)) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a.in + c0) + lane;
+        uint4 cur = ld_stream_u4(p), nxt = ld_stream_u4(p + 32);
+#pragma unroll 4
+        for (uint32_t r = 0; r < kFindChunk / 512; r++) {
+            // (the row behind the chunk's last one is readable and feeds lane 31's look-ahead there)
+            const uint4 nn = r + 2 <= kFindChunk / 512 ? ld_stream_u4(p + (r + 2) * 32) : make_uint4(0, 0, 0, 0);
+            const uint32_t n0 = __shfl_sync(kFull, lane == 0 ? nxt.x : cur.x, nl);
+            const uint32_t n1 = __shfl_sync(kFull, lane == 0 ? nxt.y : cur.y, nl);
+            const uint32_t n2 = __shfl_sync(kFull, lane == 0 ? nxt.z : cur.z, nl);
+            const uint32_t hit = find_prefilter(cur.z, cur.w, n0, n1, n2);
+            if (__any_sync(kFull, hit != 0)) {
+                const uint64_t o0 = c0 + (uint64_t)r * 512 + lane * 16;
+                emit(hit ? find_exact(a, o0, lim, cur.z, cur.w, n0, n1, n2) : 0u, o0);
+            }
+            cur = nxt;
+            nxt = nn;
+        }
+    } else {
+    for (uint32_t it0 = 0; it0 < kFindChunk / 512; it0 += 4) {
+        if (c0 + (uint64_t)it0 * 512 >= lim) break;  // warp-uniform: nothing left in this chunk
+        // four independent 16-byte loads in flight per lane; lane 0 also fetches the 16 bytes
+        // behind the fourth row (what lane 31 needs to look past its own bytes there)
+        uint4 v[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if ((u < 4 || lane == 0) && vec_ok && o0 + 16 <= in_aligned) v[u] = ld_stream_u4(a.in + o0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint64_t o0 = c0 + (uint64_t)(it0 + u) * 512 + lane * 16;  // offsets o0 .. o0+15
+            uint32_t mask = 0;                                               // bit i: o0+i is a candidate
+            // the 16 bytes that follow come from the next lane; lane 31's are lane 0's of the next
+            // row (already in registers): lane 0 offers that row to the rotating shuffle
+            const uint32_t n0 = __shfl_sync(kFull, lane == 0 ? v[u + 1].x : v[u].x, nl);
+            const uint32_t n1 = __shfl_sync(kFull, lane == 0 ? v[u + 1].y : v[u].y, nl);
+            const uint32_t n2 = __shfl_sync(kFull, lane == 0 ? v[u + 1].z : v[u].z, nl);
+            if (o0 < lim) {
+                if (vec_ok && o0 + 32 <= in_aligned) {
+                    if (find_prefilter(v[u].z, v[u].w, n0, n1, n2))
+                        mask = find_exact(a, o0, lim, v[u].z, v[u].w, n0, n1, n2);
+                } else {
+                    for (int i = 0; i < 16; i++) {
+                        const uint64_t o = o0 + i;
+                        if (o >= a.first && o < lim && o + 12 <= a.avail && a.in[o + 11] == 1 && header_plausible(a, o))
+                            mask |= 1u << i;
+                    }
+                }
+                if (o0 == proven16) mask |= 1u << (uint32_t)(a.first & 15);  // a proven start is always block 0
+            }
+            emit(mask, o0);
+        }
+    }
     }
     if (MODE != 1) {
         total = warp_sum(total);
@@ -347,7 +387,9 @@ struct DecSmem {
     int16_t rch[kMaxElems];
     int16_t rraw[kMaxElems];     // element index that fills the right slot (-1: elements ran out)
     uint16_t pre[kMaxElems];     // code prefix (depth bits) of nodes at depth <= kLutBits
-    uint8_t lvl[kMaxElems];      // depth of the node, 0xff = deeper than the table or unused
+    uint8_t lvl[2][kMaxElems];   // [d & 1][i] == d: node i sits at depth d (0xff: deeper than the table or
+                                 // unused).  Two planes: round d reads plane d & 1 and marks the children in
+                                 // the other one, so no thread reads a byte another one writes in that round
     uint16_t lut[kLutSize + 2];  // [kLutSize] = sentinel: first bit walks off a one-child root
     uint32_t sub_end[kDecThreads + 1];
     uint32_t warp_tot[kDecThreads / 32];
@@ -701,7 +743,8 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_slow(DecArgs a)
                 if (i < tl) {
                     sm.open[i] = (int16_t)run;
                     if (run == 0) atomicMin(&sm.n_eff, i);
-                    sm.lvl[i] = 0xff;
+                    sm.lvl[0][i] = 0xff;
+                    sm.lvl[1][i] = 0xff;
                 }
                 run += v[q];
             }
@@ -752,10 +795,10 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_slow(DecArgs a)
                 sm.root = 0;
                 if (sm.lch[0] >= 0 && sm.rch[0] < 0) {
                     sm.skip = 1;              // table root = the only child, one bit down
-                    sm.lvl[sm.lch[0]] = 1;
+                    sm.lvl[1][sm.lch[0]] = 1;
                     sm.pre[sm.lch[0]] = 0;
                 } else {
-                    sm.lvl[0] = 0;
+                    sm.lvl[0][0] = 0;
                     sm.pre[0] = 0;
                 }
             }
@@ -770,7 +813,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_slow(DecArgs a)
         for (uint32_t d = skip; d <= (uint32_t)kLutBits + skip; d++) {
             const uint32_t de = d - skip;  // depth below the table root
             for (uint32_t i = tid; i < n_eff; i += kDecThreads) {
-                if (sm.lvl[i] != d) continue;
+                if (sm.lvl[d & 1][i] != d) continue;
                 const uint32_t p = sm.pre[i];
                 const int l = sm.lch[i], r = sm.rch[i];
                 const bool leaf = l < 0 && r < 0;
@@ -794,7 +837,7 @@ __global__ void __launch_bounds__(kDecThreads) k_decode_slow(DecArgs a)
                     for (int side = 0; side < 2; side++) {
                         const uint32_t cp = (p << 1) | (uint32_t)side;
                         if (kids[side] >= 0) {
-                            sm.lvl[kids[side]] = (uint8_t)(d + 1);
+                            sm.lvl[(d + 1) & 1][kids[side]] = (uint8_t)(d + 1);
                             sm.pre[kids[side]] = (uint16_t)cp;
                         } else {
                             // consuming this bit walks into an absent child

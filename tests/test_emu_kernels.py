@@ -418,3 +418,34 @@ def _block_offsets(stream):
         assert rc == 0
         at += used
     return offs
+
+
+def test_emu_header_scan_interior_chunks(emu, harness):
+    """k_find streams chunks that lie entirely inside the scanned range through a specialised loop
+    (no per-row bounds tests, exact masks only for rows whose prefilter fired).  A stream of a few
+    chunks with headers at many phases, plus payload bytes that look like headers."""
+    rng = np.random.default_rng(3)
+    data = datagen.zipf(150000, 200, seed=4)
+    for bs in (3001, 20000):
+        stream = harness.oracle_encode(data, bs)
+        assert len(stream) > 4 * 32768
+        rc, got = emu.decode(stream)
+        assert (rc, got) == (0, data), bs
+    # false headers inside a payload: a foreign block (identity-like tree over raw bytes) whose
+    # payload carries the signature bytes of a plausible header at several offsets
+    from cases import hdr
+    leafs = []
+    def full(depth, prefix):
+        if depth == 8:
+            return [prefix & 0xff, -1, -1]
+        return [300 + depth] + full(depth + 1, prefix << 1) + full(depth + 1, (prefix << 1) | 1)
+    tree = full(0, 0)                                    # 8-bit identity code, binary root
+    raw = bytearray(rng.integers(0, 256, 120000, dtype=np.uint8).tobytes())
+    fake = hdr(4096, [256 + 3, 1, -1, -1])[:12]          # orig_len, tree_len = 4n+1?, tree[0] = 255+n
+    fake = (4096).to_bytes(8, "little") + (13).to_bytes(2, "little") + (258).to_bytes(2, "little")
+    for at in (5000, 33000, 40007, 70001, 99990):
+        raw[at:at + len(fake)] = fake
+    stream = hdr(len(raw), tree) + bytes(raw) + harness.oracle_encode(data[:9000], 3000)
+    rc_o, out_o, _ = harness.oracle_decode(stream)
+    rc, got = emu.decode(stream)
+    assert (rc, got) == (rc_o, out_o) and rc == 0
