@@ -630,7 +630,10 @@ def run_b200_arm(args):
         for _ in range(3):
             fn()
             fin()
-            for name, ms in ctx.kernel_times():
+            per_call: dict[str, float] = {}
+            for name, ms in ctx.kernel_times():   # (a kernel may be launched once per pass: sum them)
+                per_call[name] = per_call.get(name, 0.0) + ms
+            for name, ms in per_call.items():
                 kt.setdefault(name, []).append(ms)
         ctx.set_kernel_timing(False)
     kavg = {k: sum(v) / len(v) for k, v in kt.items()}

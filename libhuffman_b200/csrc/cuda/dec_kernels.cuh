@@ -217,11 +217,13 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
     const uint64_t lim_lean = lim < in_aligned ? lim : in_aligned;
     if (vec_ok && c0 >= a.first && c0 + kFindChunk + 544 <= lim_lean && (proven16 < c0 || proven16 >= c0 + kFindChunk)) {
         const uint4 *p = reinterpret_cast<const uint4 *>(a.in + c0) + lane;
-        uint4 cur = ld_stream_u4(p), nxt = ld_stream_u4(p + 32);
+        // (three rows in flight per lane behind the one being tested: 2 KB per warp, which is what
+        // it takes to keep HBM busy at this occupancy)
+        uint4 cur = ld_stream_u4(p), nxt = ld_stream_u4(p + 32), nx2 = ld_stream_u4(p + 64), nx3 = ld_stream_u4(p + 96);
 #pragma unroll 4
         for (uint32_t r = 0; r < kFindChunk / 512; r++) {
             // (the row behind the chunk's last one is readable and feeds lane 31's look-ahead there)
-            const uint4 nn = r + 2 <= kFindChunk / 512 ? ld_stream_u4(p + (r + 2) * 32) : make_uint4(0, 0, 0, 0);
+            const uint4 nn = r + 4 <= kFindChunk / 512 ? ld_stream_u4(p + (r + 4) * 32) : make_uint4(0, 0, 0, 0);
             const uint32_t n0 = __shfl_sync(kFull, lane == 0 ? nxt.x : cur.x, nl);
             const uint32_t n1 = __shfl_sync(kFull, lane == 0 ? nxt.y : cur.y, nl);
             const uint32_t n2 = __shfl_sync(kFull, lane == 0 ? nxt.z : cur.z, nl);
@@ -231,7 +233,9 @@ __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
                 emit(hit ? find_exact(a, o0, lim, cur.z, cur.w, n0, n1, n2) : 0u, o0);
             }
             cur = nxt;
-            nxt = nn;
+            nxt = nx2;
+            nx2 = nx3;
+            nx3 = nn;
         }
     } else {
     for (uint32_t it0 = 0; it0 < kFindChunk / 512; it0 += 4) {
