@@ -56,7 +56,6 @@ namespace {
 constexpr uint32_t kSegMax = 16384;            // bytes per segment (u16 counters suffice)
 constexpr uint64_t kMaxPassBlocks = 1u << 18;  // blocks per encode pass (bounds the workspace)
 constexpr uint64_t kW32MaxBlock = 4u << 20;    // blocks up to 4 MiB use 32-bit merge keys
-constexpr uint64_t kOverlapMinBlocks = 512;    // passes of fewer blocks are not worth a second stream
 
 struct Arena {
     uint8_t *base = nullptr;
@@ -116,9 +115,6 @@ struct huf_b200_ctx {
     int ntimed = 0;
 
     // encode call in flight
-    cudaStream_t enc_side[2] = {nullptr, nullptr};   // side streams of overlapped passes
-    cudaEvent_t enc_ev_scan[2], enc_ev_join[2], enc_ev_fork;
-    bool no_overlap = false;        // HUF_B200_OPT_NO_OVERLAP / HUF_B200_NO_OVERLAP=1: all passes on one stream
     bool enc_pending = false;
     EncArgs enc{};
     uint64_t *d_blk_off = nullptr;  // [nblocks + 1], lives in enc_ws
@@ -282,8 +278,6 @@ huf_error_t huf_b200_ctx_create(huf_b200_ctx_t **out, int device)
     const char *env = getenv("HUF_B200_ACCEPT_1025");
     c->accept_1025 = env && env[0] == '1';
     c->debug = getenv("HUF_B200_DEBUG") != nullptr;
-    env = getenv("HUF_B200_NO_OVERLAP");
-    c->no_overlap = env && env[0] == '1';
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_status, 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_result, 16 * sizeof(uint64_t));
@@ -311,14 +305,6 @@ huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx)
         if (c->d_status) cudaFree(c->d_status);
         if (c->d_result) cudaFree(c->d_result);
         if (c->h_result) cudaFreeHost(c->h_result);
-        if (c->enc_side[0]) {
-            for (int i = 0; i < 2; i++) {
-                if (c->enc_side[i]) cudaStreamDestroy(c->enc_side[i]);
-                cudaEventDestroy(c->enc_ev_scan[i]);
-                cudaEventDestroy(c->enc_ev_join[i]);
-            }
-            cudaEventDestroy(c->enc_ev_fork);
-        }
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
         delete c;
     }
@@ -441,96 +427,56 @@ huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length,
     uint64_t per_pass = nblocks < kMaxPassBlocks ? nblocks : kMaxPassBlocks;
     const uint64_t seg_cap = (1ull << 21);  // segments per pass
     if (per_pass * a.nspb > seg_cap) per_pass = seg_cap / a.nspb ? seg_cap / a.nspb : 1;
-    // Large calls run as at least four passes that alternate between two side streams with a
-    // workspace each: the code build of a pass (K2: a chain of up to 256 dependent merge steps
-    // per block, latency bound whatever the grid) then runs under the histogram and the packing
-    // of its neighbours instead of in front of an idle GPU.  Only the block-offset scans are
-    // chained (a pass's offsets start at the total of the pass before).  With per-kernel timing
-    // on, everything stays on the caller's stream so that the event times mean something.
-    const bool overlap = !c->timing && !c->no_overlap && nblocks >= 4 * kOverlapMinBlocks;
-    if (overlap && per_pass > (nblocks + 3) / 4) per_pass = (nblocks + 3) / 4;
     const uint64_t nseg_pass = per_pass * a.nspb;
-    const int nslot = overlap ? 2 : 1;
-    if (overlap && !c->enc_side[0]) {
-        for (int i = 0; i < 2; i++) {
-            CU_TRY(cudaStreamCreateWithFlags(&c->enc_side[i], cudaStreamNonBlocking));
-            CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_scan[i], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_join[i], cudaEventDisableTiming));
-        }
-        CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_fork, cudaEventDisableTiming));
-    }
 
     size_t need = 0;
+    need += Arena::padded(nseg_pass * 256 * sizeof(uint16_t));
+    need += Arena::padded(nseg_pass * sizeof(uint64_t));
+    need += Arena::padded(per_pass * sizeof(uint64_t));          // blk_bits
     need += Arena::padded(nblocks * sizeof(uint64_t));           // blk_size
     need += Arena::padded((nblocks + 1) * sizeof(uint64_t));     // blk_off
-    size_t per_slot = 0;
-    per_slot += Arena::padded(nseg_pass * 256 * sizeof(uint16_t));
-    per_slot += Arena::padded(nseg_pass * sizeof(uint64_t));
-    per_slot += Arena::padded(per_pass * sizeof(uint64_t));          // blk_bits
-    per_slot += Arena::padded(per_pass * 512 * sizeof(uint32_t));    // blk_table
-    per_slot += Arena::padded(per_pass * kTreeStride * sizeof(int16_t));
-    per_slot += Arena::padded(per_pass * 4 * sizeof(uint32_t));
-    per_slot += Arena::padded(per_pass * 256 * sizeof(uint32_t));
-    per_slot += Arena::padded(per_pass * 512 * sizeof(uint32_t));
-    need += nslot * per_slot;
+    need += Arena::padded(per_pass * 512 * sizeof(uint32_t));    // blk_table
+    need += Arena::padded(per_pass * kTreeStride * sizeof(int16_t));
+    need += Arena::padded(per_pass * 4 * sizeof(uint32_t));
+    need += Arena::padded(per_pass * 256 * sizeof(uint32_t));
+    need += Arena::padded(per_pass * 512 * sizeof(uint32_t));
     if (!c->enc_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
+    a.seg_hist = c->enc_ws.take<uint16_t>(nseg_pass * 256);
+    a.seg_bitoff = c->enc_ws.take<uint64_t>(nseg_pass);
+    a.blk_bits = c->enc_ws.take<uint64_t>(per_pass);
     a.blk_size = c->enc_ws.take<uint64_t>(nblocks);
     a.blk_off = c->enc_ws.take<uint64_t>(nblocks + 1);
+    a.blk_table = c->enc_ws.take<uint32_t>(per_pass * 512);
+    a.blk_tree = c->enc_ws.take<int16_t>(per_pass * kTreeStride);
+    a.blk_meta = c->enc_ws.take<uint32_t>(per_pass * 4);
+    a.blk_keys = c->enc_ws.take<uint32_t>(per_pass * 256);
+    a.blk_nodes = c->enc_ws.take<uint32_t>(per_pass * 512);
     a.status = c->d_status;
     c->d_blk_off = a.blk_off;
-    EncArgs slot[2];
-    for (int i = 0; i < nslot; i++) {
-        slot[i] = a;
-        slot[i].seg_hist = c->enc_ws.take<uint16_t>(nseg_pass * 256);
-        slot[i].seg_bitoff = c->enc_ws.take<uint64_t>(nseg_pass);
-        slot[i].blk_bits = c->enc_ws.take<uint64_t>(per_pass);
-        slot[i].blk_table = c->enc_ws.take<uint32_t>(per_pass * 512);
-        slot[i].blk_tree = c->enc_ws.take<int16_t>(per_pass * kTreeStride);
-        slot[i].blk_meta = c->enc_ws.take<uint32_t>(per_pass * 4);
-        slot[i].blk_keys = c->enc_ws.take<uint32_t>(per_pass * 256);
-        slot[i].blk_nodes = c->enc_ws.take<uint32_t>(per_pass * 512);
-    }
 
     CU_TRY(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), st));
     CU_TRY(cudaMemsetAsync(a.blk_off, 0, sizeof(uint64_t), st));
-    if (overlap) {
-        CU_TRY(cudaEventRecord(c->enc_ev_fork, st));
-        for (int i = 0; i < 2; i++) CU_TRY(cudaStreamWaitEvent(c->enc_side[i], c->enc_ev_fork, 0));
-    }
 
-    uint64_t pass = 0;
-    for (uint64_t blk0 = 0; blk0 < nblocks; blk0 += per_pass, pass++) {
-        EncArgs &pa = slot[overlap ? pass & 1 : 0];
-        cudaStream_t ps = overlap ? c->enc_side[pass & 1] : st;
-        pa.blk0 = blk0;
-        pa.npass = nblocks - blk0 < per_pass ? nblocks - blk0 : per_pass;
-        const uint64_t nseg = pa.npass * pa.nspb;
+    for (uint64_t blk0 = 0; blk0 < nblocks; blk0 += per_pass) {
+        a.blk0 = blk0;
+        a.npass = nblocks - blk0 < per_pass ? nblocks - blk0 : per_pass;
+        const uint64_t nseg = a.npass * a.nspb;
         const unsigned seg_grid = (unsigned)((nseg + kEncWarps - 1) / kEncWarps);
-        const unsigned bld_grid = (unsigned)((pa.npass + kBuildWarps - 1) / kBuildWarps);
+        const unsigned bld_grid = (unsigned)((a.npass + kBuildWarps - 1) / kBuildWarps);
 
-        CTX_LAUNCH(c, k_seg_hist, seg_grid, kEncWarps * 32, 0, ps, pa);
+        CTX_LAUNCH(c, k_seg_hist, seg_grid, kEncWarps * 32, 0, st, a);
         if (blocksize <= kW32MaxBlock) {
             // sort (warp per block), exact merge (lane per block), codes + tree (warp per block)
-            CTX_LAUNCH(c, k_build_sort, bld_grid, kBuildWarps * 32, 0, ps, pa);
-            CTX_LAUNCH(c, k_build_merge, (unsigned)((pa.npass + 31) / 32), 32, kMergeDyn, ps, pa);
-            CTX_LAUNCH(c, k_build_codes, bld_grid, kBuildWarps * 32, 0, ps, pa);
+            CTX_LAUNCH(c, k_build_sort, bld_grid, kBuildWarps * 32, 0, st, a);
+            CTX_LAUNCH(c, k_build_merge, (unsigned)((a.npass + 31) / 32), 32, kMergeDyn, st, a);
+            CTX_LAUNCH(c, k_build_codes, bld_grid, kBuildWarps * 32, 0, st, a);
         } else
-            CTX_LAUNCH(c, k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, ps, pa);
-        // (the offsets of this pass continue where the pass before, on the other stream, ended)
-        if (overlap && pass > 0) CU_TRY(cudaStreamWaitEvent(ps, c->enc_ev_scan[(pass - 1) & 1], 0));
-        CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, ps, pa.blk_size + blk0, pa.blk_off + blk0,
-                   pa.npass, pa.out_cap, pa.status);
-        if (overlap) CU_TRY(cudaEventRecord(c->enc_ev_scan[pass & 1], ps));
-        CTX_LAUNCH(c, k_pack, seg_grid, kEncWarps * 32, 0, ps, pa);
-        CTX_LAUNCH(c, k_pack_wide, seg_grid, kEncWarps * 32, 0, ps, pa);
+            CTX_LAUNCH(c, k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
+                   a.npass, a.out_cap, a.status);
+        CTX_LAUNCH(c, k_pack, seg_grid, kEncWarps * 32, 0, st, a);
+        CTX_LAUNCH(c, k_pack_wide, seg_grid, kEncWarps * 32, 0, st, a);
     }
-    if (overlap) {
-        for (int i = 0; i < 2; i++) {
-            CU_TRY(cudaEventRecord(c->enc_ev_join[i], c->enc_side[i]));
-            CU_TRY(cudaStreamWaitEvent(st, c->enc_ev_join[i], 0));
-        }
-    }
-    a = slot[overlap ? (pass - 1) & 1 : 0];  // (what block_offsets and the debug helpers look at)
     CU_TRY(cudaGetLastError());
     // result: total size + status, copied to the pinned mirror on the same stream
     CU_TRY(cudaMemcpyAsync(&c->h_result[0], a.blk_off + nblocks, sizeof(uint64_t),

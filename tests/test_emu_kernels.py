@@ -449,12 +449,3 @@ def test_emu_header_scan_interior_chunks(emu, harness):
     rc_o, out_o, _ = harness.oracle_decode(stream)
     rc, got = emu.decode(stream)
     assert (rc, got) == (rc_o, out_o) and rc == 0
-
-
-def test_emu_encode_passes_on_two_streams(emu, harness):
-    """2048 blocks and more: the encoder runs four or more passes that alternate between two side
-    streams and workspaces, only the block-offset scans are chained.  Same bytes as ever."""
-    data = datagen.zipf(2100 * 5 + 3, 40, seed=6)
-    want = harness.oracle_encode(data, 5)
-    rc, got = emu.encode(data, 5)
-    assert rc == 0 and got == want
