@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(EncArgs a)
         atomicMax(&a.status[0], (uint32_t)kErrFatal);
         a.status[1] = max_len;
     }
-    if (max_len > 16 && lane == 0) atomicAdd(&a.status[2], 1u);  // k_pack_wide has work
+    if ((max_len > 16 || n == 1) && lane == 0) atomicAdd(&a.status[2], 1u);  // k_pack_wide has work
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t s = lane + 32 * i;

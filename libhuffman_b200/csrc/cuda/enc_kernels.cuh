@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build(EncArgs a)
         atomicMax(&a.status[0], (uint32_t)kErrFatal);
         a.status[1] = max_len;
     }
-    if (max_len > 16 && lane == 0) atomicAdd(&a.status[2], 1u);  // k_pack_wide has work
+    if ((max_len > 16 || n == 1) && lane == 0) atomicAdd(&a.status[2], 1u);  // k_pack_wide has work
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t s = lane + 32 * i;
@@ -526,8 +526,8 @@ __device__ __forceinline__ uint32_t pack_flush_carry(const BitAcc &acc, uint32_t
     return out;
 }
 
-// General lane of K3: blocks whose longest code word exceeds kPackWideMinLen - 1 bits (the
-// fast lane in enc_pack.cuh takes all others); status[2] counts such blocks.
+// General lane of K3: blocks whose longest code word exceeds kPackWideMinLen - 1 bits, and blocks
+// of a single symbol (the fast lane in enc_pack.cuh takes all others); status[2] counts them.
 constexpr uint32_t kPackWideMinLen = 17;
 
 __global__ void __launch_bounds__(kEncWarps * 32) k_pack_wide(EncArgs a)
@@ -541,7 +541,9 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack_wide(EncArgs a)
     if (a.status[2] == 0) return;  // no deep block in this call
 
     const uint64_t bl = g / a.nspb;
-    if (a.blk_meta[bl * 4 + 1] < kPackWideMinLen) return;
+    // (blocks of one symbol have a 1-bit code: sixteen symbols of a lane do not fill a word, which
+    // the fast lane's hand-over between neighbouring lanes relies on)
+    if (a.blk_meta[bl * 4 + 1] < kPackWideMinLen && a.blk_meta[bl * 4 + 3] != 1) return;
     const uint64_t b = a.blk0 + bl;
     const uint32_t k = (uint32_t)(g % a.nspb);
     const uint64_t blen = blk_len_of(a, b);

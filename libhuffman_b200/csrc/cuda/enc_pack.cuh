@@ -1,14 +1,18 @@
 // enc_pack.cuh — K3 fast lane: bit packing for blocks whose longest code word is <= 16 bits
-// (every block of ordinary data; deeper trees take k_pack_wide in enc_kernels.cuh).
+// (every block of ordinary data; deeper trees and one-symbol blocks take k_pack_wide in
+// enc_kernels.cuh).
 //
 // One warp per segment, 16 symbols per lane and iteration.  Code words are looked up with one
-// 4-byte shared-memory load (left-aligned code in the top half, length below: the kernel is
-// bound by shared-memory wavefronts, so the table entry is kept to one bank word), two
-// neighbours are concatenated in registers (<= 32 bits), the lane's bit offset comes from a warp scan of the
-// lengths, and finished 32-bit words are OR-ed into a zeroed staging window with shared-memory
-// atomics, so lanes that share a word need no hand-over protocol.  Whole words leave as
-// coalesced big-endian 32-bit stores; only the first and last bytes of a segment, which share a
-// word with a neighbouring segment, are written byte-wise.
+// 4-byte shared-memory load (left-aligned code in the top half, length below: one bank word per
+// entry), two neighbours are concatenated in registers (<= 32 bits), the lane's bit offset comes
+// from a warp scan of the lengths.  Every lane then pushes its eight pairs through a 64-bit
+// accumulator and stores each word it COMPLETES with a plain shared-memory store: sixteen code
+// words of at least two bits fill at least one word, so every word of the window is completed
+// by exactly one lane, and what a lane leaves unfinished behind its last word boundary travels
+// to its right neighbour through one shuffle and is OR-ed into that lane's first word (lane 31's
+// remainder is the carry into the next iteration).  No atomics, no zeroing of the window.
+// Whole 16-byte lines leave as coalesced big-endian stores; only the first and last bytes of a
+// segment, which share a word with a neighbouring segment, are written byte-wise.
 // Replaces __huf_encode_block + huf_bit_write (reference src/encoder.c:85-131,
 // src/bufio.c:18-32) and the header writes (src/encoder.c:325-342).
 #pragma once
@@ -27,45 +31,6 @@ struct PackFastSmem {
     __align__(16) uint32_t stage[kEncWarps][kPackStageWords];
 };
 
-// Append the l bits of t (left aligned) to a lane's bit accumulator: `hi` is the word under
-// construction with nb bits in it, the part of t that does not fit waits in `lo` (zero between
-// calls), and a full word is OR-ed into the staging window at shared address `at`.  The flush
-// is predicated, not branched: the kernel is issue bound and lanes flush at unrelated times.
-struct PackAcc {
-    uint32_t hi, lo, nb;
-    saddr_t at;
-};
-
-__device__ __forceinline__ void acc_put_or(PackAcc &s, uint32_t t, uint32_t l)
-{
-    s.hi |= t >> s.nb;
-    s.lo = __funnelshift_r(0u, t, s.nb);
-    s.nb += l;
-#ifdef HUF_EMU
-    if (s.nb >= 32) {
-        atomicOr(reinterpret_cast<uint32_t *>(s.at), s.hi);
-        s.hi = s.lo;
-        s.lo = 0;
-        s.nb -= 32;
-        s.at += 4;
-    }
-#else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ge.u32 p, %2, 32;\n\t"
-        "@p red.shared.or.b32 [%3], %0;\n\t"
-        "@p mov.u32 %0, %1;\n\t"
-        "@p mov.u32 %1, 0;\n\t"
-        "@p sub.u32 %2, %2, 32;\n\t"
-        "@p add.u32 %3, %3, 4;\n\t"
-        "}"
-        : "+r"(s.hi), "+r"(s.lo), "+r"(s.nb), "+r"(s.at)
-        :
-        : "memory");
-#endif
-}
-
 __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
 {
     __shared__ PackFastSmem sm;
@@ -77,7 +42,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
 
     const uint64_t bl = g / a.nspb;
     const uint32_t *meta = a.blk_meta + bl * 4;
-    if (meta[1] > kPackFastMaxLen) return;  // k_pack_wide takes this block
+    if (meta[1] > kPackFastMaxLen || meta[3] == 1) return;  // k_pack_wide takes this block
     const uint64_t b = a.blk0 + bl;
     const uint32_t k = (uint32_t)(g % a.nspb);
     const uint64_t blen = blk_len_of(a, b);
@@ -121,8 +86,6 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         for (int i = lane; i < 256; i += 32) tab[i] = src[i];
     }
     uint32_t *stage = sm.stage[w];
-    const saddr_t stage_s = smem_addr(stage);
-    for (int i = lane; i < kPackStageWords / 4; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
 
     OutRange r;
@@ -133,27 +96,37 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     r.full_hi = r.b1 >> 2;
 
     // Global bit cursor, kept relative to a 16-byte line of the output so that finished lines
-    // leave as 128-bit stores.  The first byte of the segment may begin with the last bits of
-    // the previous segment's final code words: rebuild them so this warp owns the whole byte.
+    // leave as 128-bit stores: stage[0] is the first word of the line the cursor is in, q the
+    // bits of the window in front of the cursor.  Words of that line in front of the cursor's
+    // word belong to other segments (never written from here: OutRange), the bits in front of the
+    // cursor inside its word are the carry.  The first byte of the segment may begin with the last
+    // bits of the previous segment's final code words: rebuild them so this warp owns the whole
+    // byte.
     const uint64_t gbit = (pay0 << 3) + o;
     uint32_t q = (uint32_t)(gbit & 127);    // bits in front of the cursor inside its line
     uint64_t wbase = (gbit >> 7) << 2;      // output word index of stage[0] (multiple of 4)
+    uint32_t carry = 0;                     // unfinished word in front of the cursor (left aligned)
     {
         const uint32_t rb = (uint32_t)(o & 7);
-        if (rb && lane == 0) {
-            uint32_t val = 0, got = 0;
-            uint64_t idx = soff;
-            while (got < rb) {
-                idx--;
-                const uint32_t e = tab[blk_in[idx]];
-                const uint32_t l = e & 31u;
-                val |= ((e & 0xffff0000u) >> (32 - l)) << got;
-                got += l;
+        if (rb) {
+            uint32_t val = 0;
+            if (lane == 0) {
+                uint32_t got = 0;
+                uint64_t idx = soff;
+                while (got < rb) {
+                    idx--;
+                    const uint32_t e = tab[blk_in[idx]];
+                    const uint32_t l = e & 31u;
+                    val |= ((e & 0xffff0000u) >> (32 - l)) << got;
+                    got += l;
+                }
+                val &= (1u << rb) - 1u;
             }
-            val &= (1u << rb) - 1u;
-            stage[q >> 5] = val << (32 - (q & 31));  // rb != 0 implies q & 31 != 0
+            val = __shfl_sync(kFull, val, 0);
+            carry = val << (32 - (q & 31));  // rb != 0 implies q & 31 != 0
         }
     }
+    if (lane < 4) stage[lane] = 0;  // (words of the first line in front of the cursor: not ours, never output)
     __syncwarp();
 
     const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
@@ -177,7 +150,9 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
                 if ((uint32_t)j < nvalid) sym[j >> 2] |= (uint32_t)p[my0 + j] << (8 * (j & 3));
             }
         }
-        // ---- look up, concatenate neighbours (<= 32 bits), sum the lengths
+        // ---- look up, concatenate neighbours (<= 32 bits), sum the lengths.  The length sits in
+        // the low five bits of an entry: the funnel shifter takes it from there (wrap mode), and
+        // the sum of two entries still carries the sum of their lengths in its low six bits.
         uint32_t t[8], lp[8], total_l = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -188,21 +163,31 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
                 if ((uint32_t)(2 * j) >= nvalid) e0 = 0;
                 if ((uint32_t)(2 * j + 1) >= nvalid) e1 = 0;
             }
-            const uint32_t l0 = e0 & 31u;
-            t[j] = (e0 & 0xffff0000u) | ((e1 & 0xffff0000u) >> l0);
-            lp[j] = l0 + (e1 & 31u);
+            t[j] = (e0 & 0xffff0000u) | __funnelshift_r(e1 & 0xffff0000u, 0u, e0);
+            lp[j] = (e0 + e1) & 63u;
             total_l += lp[j];
         }
         const uint32_t incl = warp_incl_scan(total_l);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         const uint32_t start = q + incl - total_l;
-        PackAcc acc;
+        BitAcc acc;
         acc.hi = acc.lo = 0;
         acc.nb = start & 31;
-        acc.at = stage_s + ((start >> 5) << 2);
+        acc.widx = start >> 5;
+        const uint32_t first_widx = acc.widx;
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc_put_or(acc, t[j], lp[j]);
-        if (acc.nb) atomicOr(stage + ((acc.at - stage_s) >> 2), acc.hi);
+        for (int j = 0; j < 8; j++) acc_put(acc, stage, t[j], lp[j]);
+        if (FULL) {
+            // every lane completed at least one word: my first word still lacks the bits my left
+            // neighbour left behind its last word boundary (lane 0: the carry of the iteration
+            // before); lane 31's leftover is the next carry
+            uint32_t in = __shfl_up_sync(kFull, acc.hi, 1);
+            if (lane == 0) in = carry;
+            carry = __shfl_sync(kFull, acc.hi, 31);
+            stage[first_widx] |= in;
+        } else {
+            carry = pack_flush_carry(acc, first_widx, stage, carry);
+        }
         __syncwarp();
 
         // ---- finished 16-byte lines leave coalesced; the unfinished line stays in front
@@ -220,11 +205,11 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
                 store_word(r, w0 + 3, v.w);
             }
         }
+        // the words of the unfinished line that are complete move to the front of the window (its
+        // later words are stored by the lanes that complete them in the next iteration)
         const uint32_t keep = lane < 4 ? stage[4 * nlines + lane] : 0u;
         q = (q + total) & 127;
         wbase += 4 * nlines;
-        __syncwarp();
-        for (uint32_t i = lane; i <= nlines; i += 32) reinterpret_cast<uint4 *>(stage)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         if (lane < 4) stage[lane] = keep;
         __syncwarp();
@@ -236,8 +221,10 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     }
     for (; base < slen; base += 512) iteration(std::false_type{}, base);
 
-    // what is left of the last line: finished words and the trailing partial word, of which
-    // only the owned bytes are written
+    // what is left of the last line: finished words and the trailing partial word (the carry), of
+    // which only the owned bytes are written
+    if (lane == 0 && (q & 31)) stage[q >> 5] = carry;
+    __syncwarp();
     if (lane < 4 && 32 * (uint32_t)lane < q) store_word(r, wbase + lane, stage[lane]);
 }
 
