@@ -31,6 +31,29 @@ struct PackFastSmem {
     __align__(16) uint32_t stage[kEncWarps][kPackStageWords];
 };
 
+// A lane's bit accumulator: `cur` is the word under construction with nb (< 32) bits in it, `at`
+// the shared address it goes to once complete.  A put appends up to 32 bits (t, left aligned;
+// the sum word s carries their number in its low six bits) and stores at most one word.  What
+// does not fit becomes the new word under construction -- and is zero when nothing was stored,
+// so one select replaces the two-register hand-over -- and the byte address advances by itself.
+struct PackAcc {
+    uint32_t cur, nb;
+    saddr_t at;
+};
+
+__device__ __forceinline__ void pack_put(PackAcc &s, uint32_t t, uint32_t sum)
+{
+    const uint32_t x = t >> s.nb;                       // (nb < 32)
+    const uint32_t y = __funnelshift_r(0u, t, s.nb);    // t << (32 - nb); 0 for nb == 0
+    const uint32_t n = s.nb + sum;                      // low six bits: bits in cur after the put
+    const uint32_t w = s.cur | x;
+    const bool full = (n & 32u) != 0;
+    if (full) sts_u32(s.at, w);
+    s.cur = full ? y : w;
+    s.at += full ? 4u : 0u;
+    s.nb = n & 31u;
+}
+
 __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
 {
     __shared__ PackFastSmem sm;
@@ -86,6 +109,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         for (int i = lane; i < 256; i += 32) tab[i] = src[i];
     }
     uint32_t *stage = sm.stage[w];
+    const saddr_t stage_s = smem_addr(stage);
     __syncwarp();
 
     OutRange r;
@@ -153,7 +177,9 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         // ---- look up, concatenate neighbours (<= 32 bits), sum the lengths.  The length sits in
         // the low five bits of an entry: the funnel shifter takes it from there (wrap mode), and
         // the sum of two entries still carries the sum of their lengths in its low six bits.
-        uint32_t t[8], lp[8], total_l = 0;
+        // (entries are code << 16 | length with bits [15:5] clear: sums of entries carry the sum
+        // of the lengths in their low half whatever the codes add up to)
+        uint32_t t[8], sp[8], sum_all = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const uint32_t s0 = __byte_perm(sym[j >> 1], 0, 0x4440 + 2 * (j & 1));
@@ -164,45 +190,61 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
                 if ((uint32_t)(2 * j + 1) >= nvalid) e1 = 0;
             }
             t[j] = (e0 & 0xffff0000u) | __funnelshift_r(e1 & 0xffff0000u, 0u, e0);
-            lp[j] = (e0 + e1) & 63u;
-            total_l += lp[j];
+            sp[j] = e0 + e1;
+            sum_all += sp[j];
         }
+        const uint32_t total_l = sum_all & 0xffffu;
         const uint32_t incl = warp_incl_scan(total_l);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
         const uint32_t start = q + incl - total_l;
-        BitAcc acc;
-        acc.hi = acc.lo = 0;
-        acc.nb = start & 31;
-        acc.widx = start >> 5;
-        const uint32_t first_widx = acc.widx;
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc_put(acc, stage, t[j], lp[j]);
+        const uint32_t first_widx = start >> 5;
         if (FULL) {
+            PackAcc acc;
+            acc.cur = 0;
+            acc.nb = start & 31;
+            acc.at = stage_s + 4 * first_widx;
+#pragma unroll
+            for (int j = 0; j < 8; j++) pack_put(acc, t[j], sp[j]);
             // every lane completed at least one word: my first word still lacks the bits my left
             // neighbour left behind its last word boundary (lane 0: the carry of the iteration
             // before); lane 31's leftover is the next carry
-            uint32_t in = __shfl_up_sync(kFull, acc.hi, 1);
+            uint32_t in = __shfl_up_sync(kFull, acc.cur, 1);
             if (lane == 0) in = carry;
-            carry = __shfl_sync(kFull, acc.hi, 31);
+            carry = __shfl_sync(kFull, acc.cur, 31);
             stage[first_widx] |= in;
         } else {
+            BitAcc acc;
+            acc.hi = acc.lo = 0;
+            acc.nb = start & 31;
+            acc.widx = first_widx;
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc_put(acc, stage, t[j], sp[j] & 63u);
             carry = pack_flush_carry(acc, first_widx, stage, carry);
         }
         __syncwarp();
 
         // ---- finished 16-byte lines leave coalesced; the unfinished line stays in front
         const uint32_t nlines = (q + total) >> 7;
-        for (uint32_t L = lane; L < nlines; L += 32) {
-            const uint64_t w0 = wbase + 4 * L;
-            const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
-            if (w0 >= r.full_lo && w0 + 4 <= r.full_hi) {
-                reinterpret_cast<uint4 *>(r.out)[w0 >> 2] =
-                    make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
-            } else {
-                store_word(r, w0, v.x);
-                store_word(r, w0 + 1, v.y);
-                store_word(r, w0 + 2, v.z);
-                store_word(r, w0 + 3, v.w);
+        if (wbase >= r.full_lo && wbase + 4ull * nlines <= r.full_hi) {
+            // (every iteration but a segment's first and last: all lines lie inside the owned words)
+            uint4 *dst = reinterpret_cast<uint4 *>(r.out) + (wbase >> 2);
+            for (uint32_t L = lane; L < nlines; L += 32) {
+                const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
+                dst[L] = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+            }
+        } else {
+            for (uint32_t L = lane; L < nlines; L += 32) {
+                const uint64_t w0 = wbase + 4 * L;
+                const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
+                if (w0 >= r.full_lo && w0 + 4 <= r.full_hi) {
+                    reinterpret_cast<uint4 *>(r.out)[w0 >> 2] =
+                        make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+                } else {
+                    store_word(r, w0, v.x);
+                    store_word(r, w0 + 1, v.y);
+                    store_word(r, w0 + 2, v.z);
+                    store_word(r, w0 + 3, v.w);
+                }
             }
         }
         // the words of the unfinished line that are complete move to the front of the window (its
