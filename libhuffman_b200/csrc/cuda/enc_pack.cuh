@@ -47,10 +47,29 @@ __device__ __forceinline__ void pack_put(PackAcc &s, uint32_t t, uint32_t sum)
     const uint32_t y = __funnelshift_r(0u, t, s.nb);    // t << (32 - nb); 0 for nb == 0
     const uint32_t n = s.nb + sum;                      // low six bits: bits in cur after the put
     const uint32_t w = s.cur | x;
+#ifdef HUF_EMU
     const bool full = (n & 32u) != 0;
     if (full) sts_u32(s.at, w);
     s.cur = full ? y : w;
     s.at += full ? 4u : 0u;
+#else
+    // (spelled out: one test, a predicated store, a select and a predicated add -- the kernel is
+    // bound by the integer pipe, and the compiler's own version spends three more operations on
+    // the test and the address)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 f;\n\t"
+        "and.b32 f, %3, 32;\n\t"
+        "setp.ne.u32 p, f, 0;\n\t"
+        "@p st.shared.u32 [%1], %2;\n\t"
+        "selp.u32 %0, %4, %2, p;\n\t"
+        "@p add.u32 %1, %1, 4;\n\t"
+        "}"
+        : "=r"(s.cur), "+r"(s.at)
+        : "r"(w), "r"(n), "r"(y)
+        : "memory");
+#endif
     s.nb = n & 31u;
 }
 
