@@ -99,7 +99,10 @@ __device__ __forceinline__ void hist_u4(uint32_t *h, const uint4 &v)
 // on B200 with Zipf(1.1) input: 1 set 0.33 ms / GiB, 4 sets 0.42 ms (the skew moves the hot
 // symbols onto each other's banks), so one set it is.  Counting the segment's most frequent
 // byte value in a register (SIMD compare + popc, its atomics predicated off) is slower too
-// (0.49 ms): the extra compare work costs more than the serialised atomics it removes.
+// (0.49 ms): the extra compare work costs more than the serialised atomics it removes.  Round 2
+// tried two sets picked by lane parity with the second at index s ^ 16 (the copy of a hot low
+// symbol lands on the bank of a symbol sixteen ranks colder): 0.385 ms on Zipf, 0.46 ms on
+// uniform bytes -- the extra XOR per atomic and the second set cost more than the conflicts.
 constexpr int kHistSets = 1;
 constexpr int kHistStride = 256 + 8;
 
