@@ -25,7 +25,8 @@ with open(P / f"{tag}_launches.csv", "w") as f:
         f.write(f"{k},{n},{t / n / 1000:.1f},{100 * t / tot:.1f}\n")
 # bench + sweep
 (P / f"{tag}_bench.json").write_text((G / "bench.log").read_text())
-(P / f"{tag}_sweep.jsonl").write_text("".join(l for l in open(G / "sweep.jsonl") if l.startswith("{")))
+_line = json.loads([l for l in open(G / "bench.log") if l.startswith("{")][0])
+(P / f"{tag}_sweep.jsonl").write_text("".join(json.dumps(r) + "\n" for r in _line.get("sweep", [])))
 # ncu full
 src = subprocess.run(["ncu", "-i", str(G / "prof_dec.ncu-rep"), "--page", "source", "--print-source", "cuda,sass", "--csv",
                       "--kernel-name", "k_decode"], capture_output=True, text=True).stdout
