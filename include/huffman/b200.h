@@ -50,12 +50,18 @@ enum {
      * for contexts created afterwards (this is how huf_decode() is switched). */
     HUF_B200_OPT_ACCEPT_1025 = 1,
     /* 1: bracket every kernel launch of the following *_async calls with CUDA events on the
-     * launching stream; read them with huf_b200_kernel_times after *_finish. */
+     * launching stream; read them with huf_b200_kernel_times after *_finish.  Large encode calls
+     * then run their passes one after the other so that the times add up; value 2 keeps the
+     * pass pipeline on and reports every launch as "name@start_ms duration_ms". */
     HUF_B200_OPT_KERNEL_TIMING = 2,
     /* 1: launch the instance of the fast decode kernel that does not rely on its lookup table
      * being 8 KB aligned in the shared window (what the library falls back to by itself when
      * its probe finds the table elsewhere).  For tests. */
     HUF_B200_OPT_FORCE_LUT_ADD = 3,
+    /* 1: large encode calls run their passes one after the other on the caller's stream instead
+     * of as a pipeline over the context's side streams (env HUF_B200_NO_OVERLAP=1 sets the
+     * default).  Results are identical; for measurements and tests. */
+    HUF_B200_OPT_NO_OVERLAP = 4,
 };
 
 /* Create a context on CUDA device `device` (< 0: the current device).  Fails with

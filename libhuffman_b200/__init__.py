@@ -7,7 +7,14 @@ without a B200 the codec calls return HUF_ERROR_FATAL.
 """
 from __future__ import annotations
 
+import os
 from pathlib import Path
+
+# The encoder's pass pipeline runs over 16 CUDA streams; the driver's default of 8 hardware work
+# queues makes them alias (huf_b200.cu, huf_b200_ctx_create).  The library sets this itself when
+# it is loaded; set here as well because the package is normally imported before torch touches
+# the device while the library is loaded after.  An explicit setting of the application wins.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from .capi import (B200Lib, Config, DeviceCodec, HuffmanCLib, HuffmanError, MemStream,  # noqa: F401
                    ReadWriter)

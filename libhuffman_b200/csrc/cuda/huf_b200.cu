@@ -51,11 +51,21 @@ using namespace hufb200;
         (c)->launches++;                                                           \
     } while (0)
 
+#ifndef HUF_EMU
+// (load time: ask for enough hardware work queues for the encoder's pass pipeline, unless the
+// application has chosen a value itself)
+__attribute__((constructor)) static void huf_b200_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+#endif
+
 namespace {
 
 constexpr uint32_t kSegMax = 16384;            // bytes per segment (u16 counters suffice)
 constexpr uint64_t kMaxPassBlocks = 1u << 18;  // blocks per encode pass (bounds the workspace)
 constexpr uint64_t kW32MaxBlock = 4u << 20;    // blocks up to 4 MiB use 32-bit merge keys
+constexpr int kEncSlots = 8;                   // passes of a large encode call in flight (a workspace slot each)
+constexpr int kEncHistStreams = 2, kEncBuildStreams = 8, kEncPackStreams = 4, kEncWideStreams = 2;
+constexpr uint64_t kEncPipeMinBytes = 48ull << 20;  // smaller calls run as one pass on the caller's stream
+constexpr uint64_t kEncPipeMinPass = 4ull << 20;    // a pass of the pipeline covers at least this many input bytes
 
 struct Arena {
     uint8_t *base = nullptr;
@@ -107,6 +117,7 @@ struct huf_b200_ctx {
 
     // optional per-kernel timing (HUF_B200_OPT_KERNEL_TIMING): events around every launch
     bool timing = false;
+    bool timeline = false;          // timing value 2: keep the pass pipeline on, report start offsets too
     struct Timed {
         const char *name;
         cudaEvent_t t0, t1;
@@ -115,6 +126,16 @@ struct huf_b200_ctx {
     int ntimed = 0;
 
     // encode call in flight
+    // streams of the pipelined encode: histograms (low priority), code builds (high: short
+    // grids of latency-bound warps that must not queue behind thousands of CTAs), packing
+    cudaStream_t enc_hist_st[kEncHistStreams] = {}, enc_build_st[kEncBuildStreams] = {}, enc_pack_st[kEncPackStreams] = {},
+                 enc_wide_st[kEncWideStreams] = {};
+    cudaEvent_t enc_ev_hist[kEncSlots], enc_ev_build[kEncSlots], enc_ev_pack[kEncSlots], enc_ev_wide[kEncSlots], enc_ev_fork;
+    bool enc_side_ready = false;
+    bool no_overlap = false;        // HUF_B200_OPT_NO_OVERLAP / HUF_B200_NO_OVERLAP=1: passes one after the other on one stream
+    uint64_t enc_pipe_min = kEncPipeMinBytes;       // (HUF_B200_ENC_PIPE_MIN, HUF_B200_ENC_PIPE_PASS, HUF_B200_ENC_SLOTS:
+    uint64_t enc_pipe_min_pass = kEncPipeMinPass;   //  the pipeline's thresholds in bytes and its slot count, for tests)
+    int enc_slots = kEncSlots;
     bool enc_pending = false;
     EncArgs enc{};
     uint64_t *d_blk_off = nullptr;  // [nblocks + 1], lives in enc_ws
@@ -136,6 +157,7 @@ struct huf_b200_ctx {
     bool lut_or = true;             // k_decode's table is 8 KB aligned in the shared window (probed)
     bool force_lut_add = false;     // HUF_B200_OPT_FORCE_LUT_ADD: always launch k_decode_unaligned
     int fast_per_sm = 1;
+    int fast_pad = 0;
     uint64_t dec_stage_want = 80 * 1024;  // payload bytes of one block staged in shared memory
 
     pipe::PipeState pipe;           // streams, events and cached buffers of the host-buffer lanes
@@ -278,6 +300,18 @@ huf_error_t huf_b200_ctx_create(huf_b200_ctx_t **out, int device)
     const char *env = getenv("HUF_B200_ACCEPT_1025");
     c->accept_1025 = env && env[0] == '1';
     c->debug = getenv("HUF_B200_DEBUG") != nullptr;
+    env = getenv("HUF_B200_NO_OVERLAP");
+    c->no_overlap = env && env[0] == '1';
+    // The pass pipeline of the encoder uses 16 streams.  With the driver's default of 8 hardware
+    // work queues they alias and serialise falsely (measured: 1.53 ms against 1.41 ms on one
+    // stream and 1.33 ms with 32 queues), so the pipeline is only used when the process runs
+    // with CUDA_DEVICE_MAX_CONNECTIONS >= 16 (this library sets 32 when it is loaded, which
+    // takes effect if that happens before CUDA is initialised).
+    env = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+    if (!env || atoi(env) < 16) c->no_overlap = true;
+    if ((env = getenv("HUF_B200_ENC_PIPE_MIN")) && atoll(env) > 0) c->enc_pipe_min = (uint64_t)atoll(env);
+    if ((env = getenv("HUF_B200_ENC_PIPE_PASS")) && atoll(env) > 0) c->enc_pipe_min_pass = (uint64_t)atoll(env);
+    if ((env = getenv("HUF_B200_ENC_SLOTS")) && atoi(env) >= 1 && atoi(env) <= kEncSlots) c->enc_slots = atoi(env);
     cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_status, 4 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_result, 16 * sizeof(uint64_t));
@@ -305,6 +339,19 @@ huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx)
         if (c->d_status) cudaFree(c->d_status);
         if (c->d_result) cudaFree(c->d_result);
         if (c->h_result) cudaFreeHost(c->h_result);
+        if (c->enc_side_ready) {
+            for (int i = 0; i < kEncHistStreams; i++) cudaStreamDestroy(c->enc_hist_st[i]);
+            for (int i = 0; i < kEncBuildStreams; i++) cudaStreamDestroy(c->enc_build_st[i]);
+            for (int i = 0; i < kEncPackStreams; i++) cudaStreamDestroy(c->enc_pack_st[i]);
+            for (int i = 0; i < kEncWideStreams; i++) cudaStreamDestroy(c->enc_wide_st[i]);
+            for (int i = 0; i < kEncSlots; i++) {
+                cudaEventDestroy(c->enc_ev_hist[i]);
+                cudaEventDestroy(c->enc_ev_build[i]);
+                cudaEventDestroy(c->enc_ev_pack[i]);
+                cudaEventDestroy(c->enc_ev_wide[i]);
+            }
+            cudaEventDestroy(c->enc_ev_fork);
+        }
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
         delete c;
     }
@@ -321,10 +368,14 @@ huf_error_t huf_b200_ctx_set_option(huf_b200_ctx_t *ctx, int option, int64_t val
         return HUF_ERROR_SUCCESS;
     case HUF_B200_OPT_KERNEL_TIMING:
         ctx->timing = value != 0;
+        ctx->timeline = value == 2;
         return HUF_ERROR_SUCCESS;
     case HUF_B200_OPT_FORCE_LUT_ADD:
         ctx->force_lut_add = value != 0;
         ctx->fast_ready = false;  // choose the kernel instance again
+        return HUF_ERROR_SUCCESS;
+    case HUF_B200_OPT_NO_OVERLAP:
+        ctx->no_overlap = value != 0;
         return HUF_ERROR_SUCCESS;
     default:
         return HUF_ERROR_INVALID_ARGUMENT;
@@ -357,14 +408,23 @@ huf_error_t huf_b200_kernel_times(huf_b200_ctx_t *c, char *buf, uint64_t buflen)
     size_t at = 0;
     buf[0] = 0;
     for (int i = 0; i < c->ntimed; i++) {
-        float ms = 0.f;
+        float ms = 0.f, from0 = 0.f;
         cudaEventSynchronize(c->timed[i].t1);
         cudaEventElapsedTime(&ms, c->timed[i].t0, c->timed[i].t1);
-        cudaEventDestroy(c->timed[i].t0);
-        cudaEventDestroy(c->timed[i].t1);
-        int n = snprintf(buf + at, buflen - at, "%s %.6f\n", c->timed[i].name, (double)ms);
+        int n;
+        if (c->timeline) {
+            // (timeline mode: "name@start duration", the start relative to the first launch)
+            cudaEventElapsedTime(&from0, c->timed[0].t0, c->timed[i].t0);
+            n = snprintf(buf + at, buflen - at, "%s@%.4f %.6f\n", c->timed[i].name, (double)from0, (double)ms);
+        } else {
+            n = snprintf(buf + at, buflen - at, "%s %.6f\n", c->timed[i].name, (double)ms);
+        }
         if (n < 0 || (size_t)n >= buflen - at) break;
         at += (size_t)n;
+    }
+    for (int i = 0; i < c->ntimed; i++) {
+        cudaEventDestroy(c->timed[i].t0);
+        cudaEventDestroy(c->timed[i].t1);
     }
     c->ntimed = 0;
     return HUF_ERROR_SUCCESS;
@@ -427,56 +487,148 @@ huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length,
     uint64_t per_pass = nblocks < kMaxPassBlocks ? nblocks : kMaxPassBlocks;
     const uint64_t seg_cap = (1ull << 21);  // segments per pass
     if (per_pass * a.nspb > seg_cap) per_pass = seg_cap / a.nspb ? seg_cap / a.nspb : 1;
+    // Large calls run as a pipeline of passes (block ranges) over workspace slots.  The code
+    // build of a pass (K2: per block a chain of up to 255 dependent merge steps, latency bound
+    // whatever the grid: 0.3 ms of a 1.4 ms encode at 5-65 % occupancy) then runs under the
+    // histograms and the packing of its neighbours.  Three kinds of streams: the histograms of
+    // all passes go first (low priority, in pass order), the builds follow them on high-priority
+    // streams (a build is a few hundred latency-bound warps and the one-CTA offset scan: queued
+    // at equal priority behind the thousands of CTAs of K1/K3 every one of its launches waited
+    // ~0.1 ms for a free slot, measured with the timeline mode of HUF_B200_OPT_KERNEL_TIMING),
+    // and the packing of a pass starts when its build is done.  Across passes only the
+    // block-offset scan chains (the offsets of a pass start at the total of the pass before).
+    // With per-kernel timing on everything stays on the caller's stream so that event times add
+    // up (value 2 keeps the pipeline and reports start offsets instead).
+    bool overlap = (!c->timing || c->timeline) && !c->no_overlap && length >= c->enc_pipe_min && nblocks >= 2 * (uint64_t)kEncSlots;
+    if (overlap) {
+        uint64_t want = (nblocks + kEncSlots - 1) / kEncSlots;
+        const uint64_t min_blocks = (c->enc_pipe_min_pass + blocksize - 1) / blocksize;
+        if (want < min_blocks) want = min_blocks;
+        if (want < per_pass) per_pass = want;
+        if (per_pass >= nblocks) overlap = false;
+    }
     const uint64_t nseg_pass = per_pass * a.nspb;
+    const uint64_t npasses = (nblocks + per_pass - 1) / per_pass;
+    const int nslot = overlap ? (int)(npasses < (uint64_t)c->enc_slots ? npasses : (uint64_t)c->enc_slots) : 1;
+    if (overlap && !c->enc_side_ready) {
+        int prio_lo = 0, prio_hi = 0;  // (numerically: highest priority = smallest value)
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
+        for (int i = 0; i < kEncHistStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&c->enc_hist_st[i], cudaStreamNonBlocking, prio_lo));
+        for (int i = 0; i < kEncBuildStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&c->enc_build_st[i], cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < kEncPackStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&c->enc_pack_st[i], cudaStreamNonBlocking, prio_mid));
+        for (int i = 0; i < kEncWideStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&c->enc_wide_st[i], cudaStreamNonBlocking, prio_mid));
+        for (int i = 0; i < kEncSlots; i++) {
+            CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_hist[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_build[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_pack[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_wide[i], cudaEventDisableTiming));
+        }
+        CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_fork, cudaEventDisableTiming));
+        c->enc_side_ready = true;
+    }
 
     size_t need = 0;
-    need += Arena::padded(nseg_pass * 256 * sizeof(uint16_t));
-    need += Arena::padded(nseg_pass * sizeof(uint64_t));
-    need += Arena::padded(per_pass * sizeof(uint64_t));          // blk_bits
     need += Arena::padded(nblocks * sizeof(uint64_t));           // blk_size
     need += Arena::padded((nblocks + 1) * sizeof(uint64_t));     // blk_off
-    need += Arena::padded(per_pass * 512 * sizeof(uint32_t));    // blk_table
-    need += Arena::padded(per_pass * kTreeStride * sizeof(int16_t));
-    need += Arena::padded(per_pass * 4 * sizeof(uint32_t));
-    need += Arena::padded(per_pass * 256 * sizeof(uint32_t));
-    need += Arena::padded(per_pass * 512 * sizeof(uint32_t));
+    size_t per_slot = 0;
+    per_slot += Arena::padded(nseg_pass * 256 * sizeof(uint16_t));
+    per_slot += Arena::padded(nseg_pass * sizeof(uint64_t));
+    per_slot += Arena::padded(per_pass * sizeof(uint64_t));          // blk_bits
+    per_slot += Arena::padded(per_pass * 512 * sizeof(uint32_t));    // blk_table
+    per_slot += Arena::padded(per_pass * kTreeStride * sizeof(int16_t));
+    per_slot += Arena::padded(per_pass * 4 * sizeof(uint32_t));
+    per_slot += Arena::padded(per_pass * 256 * sizeof(uint32_t));
+    per_slot += Arena::padded(per_pass * 512 * sizeof(uint32_t));
+    need += (size_t)nslot * per_slot;
     if (!c->enc_ws.reserve(need)) return HUF_ERROR_MEMORY_ALLOCATION;
-    a.seg_hist = c->enc_ws.take<uint16_t>(nseg_pass * 256);
-    a.seg_bitoff = c->enc_ws.take<uint64_t>(nseg_pass);
-    a.blk_bits = c->enc_ws.take<uint64_t>(per_pass);
     a.blk_size = c->enc_ws.take<uint64_t>(nblocks);
     a.blk_off = c->enc_ws.take<uint64_t>(nblocks + 1);
-    a.blk_table = c->enc_ws.take<uint32_t>(per_pass * 512);
-    a.blk_tree = c->enc_ws.take<int16_t>(per_pass * kTreeStride);
-    a.blk_meta = c->enc_ws.take<uint32_t>(per_pass * 4);
-    a.blk_keys = c->enc_ws.take<uint32_t>(per_pass * 256);
-    a.blk_nodes = c->enc_ws.take<uint32_t>(per_pass * 512);
     a.status = c->d_status;
     c->d_blk_off = a.blk_off;
+    EncArgs slot[kEncSlots];
+    for (int i = 0; i < nslot; i++) {
+        slot[i] = a;
+        slot[i].seg_hist = c->enc_ws.take<uint16_t>(nseg_pass * 256);
+        slot[i].seg_bitoff = c->enc_ws.take<uint64_t>(nseg_pass);
+        slot[i].blk_bits = c->enc_ws.take<uint64_t>(per_pass);
+        slot[i].blk_table = c->enc_ws.take<uint32_t>(per_pass * 512);
+        slot[i].blk_tree = c->enc_ws.take<int16_t>(per_pass * kTreeStride);
+        slot[i].blk_meta = c->enc_ws.take<uint32_t>(per_pass * 4);
+        slot[i].blk_keys = c->enc_ws.take<uint32_t>(per_pass * 256);
+        slot[i].blk_nodes = c->enc_ws.take<uint32_t>(per_pass * 512);
+    }
 
     CU_TRY(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), st));
     CU_TRY(cudaMemsetAsync(a.blk_off, 0, sizeof(uint64_t), st));
+    if (overlap) CU_TRY(cudaEventRecord(c->enc_ev_fork, st));  // the side streams start behind the caller's work
 
-    for (uint64_t blk0 = 0; blk0 < nblocks; blk0 += per_pass) {
-        a.blk0 = blk0;
-        a.npass = nblocks - blk0 < per_pass ? nblocks - blk0 : per_pass;
-        const uint64_t nseg = a.npass * a.nspb;
+    uint64_t pass = 0;
+    for (uint64_t blk0 = 0; blk0 < nblocks; blk0 += per_pass, pass++) {
+        const int si = overlap ? (int)(pass % (uint64_t)nslot) : 0;
+        const int sprev = overlap ? (int)((pass + (uint64_t)nslot - 1) % (uint64_t)nslot) : 0;
+        EncArgs &pa = slot[si];
+        cudaStream_t hs = overlap ? c->enc_hist_st[pass % kEncHistStreams] : st;
+        cudaStream_t bs = overlap ? c->enc_build_st[pass % kEncBuildStreams] : st;
+        cudaStream_t ps = overlap ? c->enc_pack_st[pass % kEncPackStreams] : st;
+        cudaStream_t ws = overlap ? c->enc_wide_st[pass % kEncWideStreams] : st;
+        pa.blk0 = blk0;
+        pa.npass = nblocks - blk0 < per_pass ? nblocks - blk0 : per_pass;
+        const uint64_t nseg = pa.npass * pa.nspb;
         const unsigned seg_grid = (unsigned)((nseg + kEncWarps - 1) / kEncWarps);
-        const unsigned bld_grid = (unsigned)((a.npass + kBuildWarps - 1) / kBuildWarps);
+        const unsigned bld_grid = (unsigned)((pa.npass + kBuildWarps - 1) / kBuildWarps);
+        const bool reuse = overlap && pass >= (uint64_t)nslot;  // the slot has served an earlier pass
 
-        CTX_LAUNCH(c, k_seg_hist, seg_grid, kEncWarps * 32, 0, st, a);
+        // K1.  (A slot's histograms are free once the build of its previous pass has read them.)
+        if (overlap && pass < (uint64_t)kEncHistStreams) CU_TRY(cudaStreamWaitEvent(hs, c->enc_ev_fork, 0));
+        if (reuse) CU_TRY(cudaStreamWaitEvent(hs, c->enc_ev_build[si], 0));
+        CTX_LAUNCH(c, k_seg_hist, seg_grid, kEncWarps * 32, 0, hs, pa);
+        if (overlap) {
+            CU_TRY(cudaEventRecord(c->enc_ev_hist[si], hs));
+            // K2 behind K1; a slot's tables are free once its previous pass has been packed
+            CU_TRY(cudaStreamWaitEvent(bs, c->enc_ev_hist[si], 0));
+            if (reuse) {
+                CU_TRY(cudaStreamWaitEvent(bs, c->enc_ev_pack[si], 0));
+                CU_TRY(cudaStreamWaitEvent(bs, c->enc_ev_wide[si], 0));
+            }
+        }
         if (blocksize <= kW32MaxBlock) {
             // sort (warp per block), exact merge (lane per block), codes + tree (warp per block)
-            CTX_LAUNCH(c, k_build_sort, bld_grid, kBuildWarps * 32, 0, st, a);
-            CTX_LAUNCH(c, k_build_merge, (unsigned)((a.npass + 31) / 32), 32, kMergeDyn, st, a);
-            CTX_LAUNCH(c, k_build_codes, bld_grid, kBuildWarps * 32, 0, st, a);
+            CTX_LAUNCH(c, k_build_sort, bld_grid, kBuildWarps * 32, 0, bs, pa);
+            CTX_LAUNCH(c, k_build_merge, (unsigned)((pa.npass + 31) / 32), 32, kMergeDyn, bs, pa);
+            CTX_LAUNCH(c, k_build_codes, bld_grid, kBuildWarps * 32, 0, bs, pa);
         } else
-            CTX_LAUNCH(c, k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, st, a);
-        CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, st, a.blk_size + blk0, a.blk_off + blk0,
-                   a.npass, a.out_cap, a.status);
-        CTX_LAUNCH(c, k_pack, seg_grid, kEncWarps * 32, 0, st, a);
-        CTX_LAUNCH(c, k_pack_wide, seg_grid, kEncWarps * 32, 0, st, a);
+            CTX_LAUNCH(c, k_build<uint64_t>, bld_grid, kBuildWarps * 32, 0, bs, pa);
+        // (the offsets of this pass continue where the pass before, on another stream, ended)
+        if (overlap && pass > 0) CU_TRY(cudaStreamWaitEvent(bs, c->enc_ev_build[sprev], 0));
+        CTX_LAUNCH(c, k_scan_sizes, 1, kScanThreads, 0, bs, pa.blk_size + blk0, pa.blk_off + blk0,
+                   pa.npass, pa.out_cap, pa.status);
+        if (overlap) {
+            CU_TRY(cudaEventRecord(c->enc_ev_build[si], bs));
+            CU_TRY(cudaStreamWaitEvent(ps, c->enc_ev_build[si], 0));
+            CU_TRY(cudaStreamWaitEvent(ws, c->enc_ev_build[si], 0));
+        }
+        // (the two packing kernels take disjoint blocks -- code words of up to 16 bits / longer --
+        // and nearly always one of them finds nothing to do: side by side, so that an empty grid
+        // queueing for SM slots does not hold up the packing stream)
+        CTX_LAUNCH(c, k_pack, seg_grid, kEncWarps * 32, 0, ps, pa);
+        if (overlap) CU_TRY(cudaEventRecord(c->enc_ev_pack[si], ps));
+        CTX_LAUNCH(c, k_pack_wide, seg_grid, kEncWarps * 32, 0, ws, pa);
+        if (overlap) CU_TRY(cudaEventRecord(c->enc_ev_wide[si], ws));
     }
+    if (overlap) {
+        // join: the caller's stream continues behind the packing of every slot's last pass
+        // (everything else of the call lies in front of those by the event chain)
+        for (int i = 0; i < nslot; i++) {
+            CU_TRY(cudaStreamWaitEvent(st, c->enc_ev_pack[i], 0));
+            CU_TRY(cudaStreamWaitEvent(st, c->enc_ev_wide[i], 0));
+        }
+    }
+    a = slot[overlap ? (int)((pass - 1) % (uint64_t)nslot) : 0];  // (what block_offsets and the debug helpers look at)
     CU_TRY(cudaGetLastError());
     // result: total size + status, copied to the pinned mirror on the same stream
     CU_TRY(cudaMemcpyAsync(&c->h_result[0], a.blk_off + nblocks, sizeof(uint64_t),
@@ -641,12 +793,15 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
             } else {
                 c->lut_or = false;
             }
+            // (HUF_B200_DEC_PAD: unused extra shared memory per CTA -- an occupancy experiment knob)
+            const char *pad_env = getenv("HUF_B200_DEC_PAD");
+            c->fast_pad = pad_env ? atoi(pad_env) & ~15 : 0;
             CU_TRY(cudaFuncSetAttribute(k_decode_unaligned, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kFastDyn));
+                                        kFastDyn + c->fast_pad));
             CU_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kFastDyn));
+                                        kFastDyn + c->fast_pad));
             int fper = 1;
-            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fper, k_decode, kFT, kFastDyn));
+            CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fper, k_decode, kFT, kFastDyn + c->fast_pad));
             c->fast_per_sm = fper < 1 ? 1 : fper;
             CU_TRY(cudaFuncSetAttribute(k_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeDyn));
             c->fast_ready = true;
@@ -655,9 +810,9 @@ huf_error_t dec_enqueue(huf_b200_ctx *c, uint64_t first, uint64_t out_base, bool
         // declines goes through the general lane
         CTX_LAUNCH(c, k_tree, c->sm_count * 6, 32, kTreeDyn, st, a);
         if (c->lut_or)
-            CTX_LAUNCH(c, k_decode, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
+            CTX_LAUNCH(c, k_decode, c->sm_count * c->fast_per_sm, kFT, kFastDyn + c->fast_pad, st, a);
         else
-            CTX_LAUNCH(c, k_decode_unaligned, c->sm_count * c->fast_per_sm, kFT, kFastDyn, st, a);
+            CTX_LAUNCH(c, k_decode_unaligned, c->sm_count * c->fast_per_sm, kFT, kFastDyn + c->fast_pad, st, a);
         CTX_LAUNCH(c, k_decode_slow, c->sm_count * per_sm, kDecThreads, c->dec_stage, st, a);
         CTX_LAUNCH(c, k_verify, 1, kScanThreads, 0, st, a);
     }

@@ -449,3 +449,33 @@ def test_emu_header_scan_interior_chunks(emu, harness):
     rc_o, out_o, _ = harness.oracle_decode(stream)
     rc, got = emu.decode(stream)
     assert (rc, got) == (rc_o, out_o) and rc == 0
+
+
+def test_emu_encode_pass_pipeline(emu, harness, monkeypatch):
+    """The pipelined encode (passes over workspace slots and side streams, huf_b200.cu
+    encode_enqueue) with thresholds shrunk so that a small input runs 8 passes over 3 slots:
+    slot reuse, the chained offset scan, a ragged last pass.  Byte-equal to the oracle and to the
+    single-stream order."""
+    monkeypatch.setenv("HUF_B200_ENC_PIPE_MIN", "1")
+    monkeypatch.setenv("HUF_B200_ENC_PIPE_PASS", "1")
+    monkeypatch.setenv("HUF_B200_ENC_SLOTS", "3")
+    data = datagen.zipf(1000 * 61 + 17, 200, seed=77)
+    bs = 1000   # 62 blocks: 8 passes of 8 blocks, the last of 6 (ragged block at the end)
+    want = harness.oracle_encode(data, bs)
+    for no_overlap in (False, True):
+        codec = DeviceCodec(emu)
+        try:
+            emu.check(emu.dll.huf_b200_ctx_set_option(codec.ctx, 4, int(no_overlap)), "set_option")
+            src = C.create_string_buffer(data, len(data))
+            cap = codec.encode_bound(len(data), bs)
+            dst = C.create_string_buffer(cap)
+            codec.encode_async(C.addressof(src), len(data), bs, C.addressof(dst), cap)
+            n = codec.encode_finish()
+            assert dst.raw[:n] == want, no_overlap
+            launches = codec.launches()
+            assert launches == (8 * 7 if not no_overlap else 7), launches   # 7 kernels per pass
+            ptr, nb = codec.block_offsets()
+            offs = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), (nb + 1,)).copy()
+            assert nb == 62 and offs[0] == 0 and offs[-1] == n
+        finally:
+            codec.close()

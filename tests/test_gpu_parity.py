@@ -555,3 +555,42 @@ def test_fast_lane_without_table_alignment(lib, harness, torch_cuda):
         assert "k_decode_unaligned" in names and "k_decode" not in names
     finally:
         dec.close()
+
+
+@pytest.mark.parametrize("shape,bs,mib,slots", [("zipf255", 65536, 160, 8), ("zipf255", 4096, 96, 3),
+                                                 ("fibonacci", 1 << 20, 160, 2)])
+def test_pipelined_encode_equals_single_stream(lib, harness, torch_cuda, monkeypatch, shape, bs, mib, slots):
+    """Large encode calls run as a staggered pipeline of passes over side streams
+    (huf_b200.cu encode_enqueue).  The stream must be byte-equal to the one-stream order, repeated
+    calls must agree (no workspace slot is reused too early), sampled blocks equal the oracle,
+    and the stream decodes back."""
+    torch = torch_cuda
+    monkeypatch.setenv("HUF_B200_ENC_SLOTS", str(slots))
+    monkeypatch.setenv("HUF_B200_ENC_PIPE_PASS", str(8 << 20))   # up to 8 passes over `slots` slots
+    n = (mib << 20) + 12345
+    if shape == "zipf255":
+        x = datagen.zipf_torch(n, "cuda", 255, seed=21)
+    else:   # 8 MiB of the skewed shape, tiled (blocks repeat, passes do not line up with the tile)
+        tile = np.frombuffer(datagen.fibonacci(8 << 20, bs, seed=4), dtype=np.uint8)
+        x = torch.from_numpy(np.resize(tile, n).copy()).cuda()
+    piped = DeviceCodec(lib, 0)
+    plain = DeviceCodec(lib, 0)
+    try:
+        lib.check(lib.dll.huf_b200_ctx_set_option(plain.ctx, 4, 1), "set_option")
+        ref, offs = dev_encode(torch, plain, x, bs)
+        ref = ref.clone()
+        for _ in range(3):
+            got, offs2 = dev_encode(torch, piped, x, bs)
+            assert got.numel() == ref.numel() and torch.equal(got, ref)
+            assert np.array_equal(offs, offs2)
+        nb = len(offs) - 1
+        rng = np.random.default_rng(5)
+        for b in [0, nb - 1, *rng.integers(0, nb, 6).tolist()]:
+            block = x[b * bs:(b + 1) * bs].cpu().numpy().tobytes()
+            assert ref[int(offs[b]):int(offs[b + 1])].cpu().numpy().tobytes() == harness.oracle_encode(block, 0), b
+        piped.set_accept_1025(True)
+        rc, back, used = dev_decode(torch, piped, got, n)
+        assert rc == 0 and used == got.numel() and torch.equal(back, x)
+    finally:
+        piped.close()
+        plain.close()
