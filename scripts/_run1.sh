@@ -1,4 +1,3 @@
-python scripts/phase_prof.py run zipf255 1024 2>&1 | tail -14
-for shape in zipf255 geometric fibonacci uniform english; do
-  python scripts/kernel_times.py $shape 1024 65536 2>&1 | grep -E "k_decode |mib"
-done
+python scripts/kernel_times.py zipf255 1024 65536 2>&1 | grep -E "k_tree|k_decode |mib"
+python scripts/kernel_times.py zipf255 1024 4096 2>&1 | grep -E "k_tree|k_decode |mib"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --no-header -p no:cacheprovider -k "foreign or golden or c_api or matrix" 2>&1 | tail -3
