@@ -408,6 +408,18 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// Shared address of staged word `idx` (tests/emu: addresses are 64-bit host pointers there, which
+// a 32-bit multiply-add would cut off -- harmless in the main thread of a non-PIE interpreter,
+// whose heap lies below 4 GB, fatal in the worker threads of the multi-device host lanes).
+__device__ __forceinline__ saddr_t saddr_word(uint32_t idx, saddr_t base)
+{
+#ifdef HUF_EMU
+    return base + (saddr_t)idx * 4u;
+#else
+    return mad_u32(idx, 4u, base);
+#endif
+}
+
 // Table offset for the bulk walk.  The walk is bound by the integer ALU pipe (shifts, logic,
 // compares: one warp instruction every other cycle) while the multiply-add pipe idles, so the
 // right shift by 18 is done as the high half of a multiplication by 2^14; the factor comes
@@ -943,7 +955,7 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
                             // window advance by 0, 1 or 2 words (the word index travels with the
                             // loop, the address is a multiply-add: both off the integer ALU pipe)
                             const uint32_t nw = np >> 5;
-                            win_step(b, mad_u32(nw, 4u, sw_s), nw - pw);
+                            win_step(b, saddr_word(nw, sw_s), nw - pw);
                             pw = nw;
                             p = np;
                         } while (p <= bulk_last);

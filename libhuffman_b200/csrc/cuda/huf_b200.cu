@@ -504,6 +504,10 @@ huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length,
         uint64_t want = (nblocks + kEncSlots - 1) / kEncSlots;
         const uint64_t min_blocks = (c->enc_pipe_min_pass + blocksize - 1) / blocksize;
         if (want < min_blocks) want = min_blocks;
+        // (very large calls: passes of at most 256 MiB over the eight slots in turn, so that the
+        // workspace stays small whatever the call size)
+        const uint64_t max_blocks = ((256ull << 20) + blocksize - 1) / blocksize;
+        if (want > max_blocks) want = max_blocks;
         if (want < per_pass) per_pass = want;
         if (per_pass >= nblocks) overlap = false;
     }
