@@ -162,6 +162,10 @@ typedef struct huf_b200_sink {
     huf_error_t (*commit)(void *arg, uint64_t count);
     huf_error_t (*push)(void *arg, const void *src, uint64_t count);
     void *arg;
+    /* Optional, lending sinks only: where the next byte goes and how many bytes fit there
+     * without the buffer moving.  When that range is page-locked (huf_b200_host_register) the
+     * lanes copy device -> sink directly into it and only call commit. */
+    huf_error_t (*room)(void *arg, void **dst, uint64_t *avail);
 } huf_b200_sink_t;
 
 /* huf_encode below the streams: `length` bytes of `src` in blocks of `blocksize` (0 => one
@@ -217,6 +221,17 @@ huf_error_t huf_b200_dev_alloc(void **d_ptr, uint64_t bytes);
 huf_error_t huf_b200_dev_free(void *d_ptr);
 huf_error_t huf_b200_copy_h2d(void *d_dst, const void *h_src, uint64_t bytes);
 huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes);
+/* Page-lock / release caller memory for direct DMA (cudaHostRegister).  The host lanes use a
+ * contiguous source or a lending sink in place -- no bounce copy through their own pinned
+ * buffers -- when its bytes are page-locked.  Registering costs ~0.3 s per GiB (and releasing
+ * about as much), so it only pays for buffers that live through many calls: huf_memopen streams
+ * are registered by the library from their HUF_B200_PIN_AFTER-th codec call on (default 4;
+ * 0 = never) and released when they grow or are closed. */
+huf_error_t huf_b200_host_register(void *ptr, uint64_t bytes);
+huf_error_t huf_b200_host_unregister(void *ptr);
+/* Counter for benches/tests: spans and results the host lanes copied straight from / into
+ * page-locked caller memory since the library was loaded. */
+uint64_t huf_b200_direct_copy_count(void);
 /* Number of visible CUDA devices (0 when the driver/GPU is missing). */
 int huf_b200_device_count(void);
 

@@ -182,6 +182,12 @@ class B200Lib(HuffmanCLib):
         d.huf_b200_decode_hint_offsets.argtypes = [vp, vp, u64]
         d.huf_b200_last_slow_blocks.restype = u64
         d.huf_b200_last_slow_blocks.argtypes = [vp]
+        d.huf_b200_direct_copy_count.restype = u64
+        d.huf_b200_direct_copy_count.argtypes = []
+        d.huf_b200_host_register.argtypes = [vp, u64]
+        d.huf_b200_host_register.restype = C.c_int
+        d.huf_b200_host_unregister.argtypes = [vp]
+        d.huf_b200_host_unregister.restype = C.c_int
         d.huf_b200_kernel_times.argtypes = [vp, C.c_char_p, u64]
         d.huf_b200_kernel_times.restype = C.c_int
         d.huf_b200_dev_alloc.argtypes = [C.POINTER(vp), u64]

@@ -1108,6 +1108,71 @@ huf_error_t huf_b200_copy_d2h(void *h_dst, const void *d_src, uint64_t bytes)
 
 
 // ------------------------------------------------------------------------------------------
+// page-locked caller memory
+// ------------------------------------------------------------------------------------------
+
+namespace {
+struct PinnedRanges {
+    std::mutex mu;
+    struct R {
+        const uint8_t *base;
+        uint64_t len;
+    };
+    std::vector<R> v;
+    bool covers(const void *p, uint64_t len)
+    {
+        const uint8_t *q = static_cast<const uint8_t *>(p);
+        std::lock_guard<std::mutex> lock(mu);
+        for (const R &r : v)
+            if (q >= r.base && q + len <= r.base + r.len) return true;
+        return false;
+    }
+};
+PinnedRanges g_pinned;
+std::atomic<uint64_t> g_direct_copies{0};  // spans / results the lanes moved without a bounce copy
+}  // namespace
+
+uint64_t huf_b200_direct_copy_count(void) { return g_direct_copies.load(); }
+
+huf_error_t huf_b200_host_register(void *ptr, uint64_t bytes)
+{
+    if (!ptr || !bytes) return HUF_ERROR_INVALID_ARGUMENT;
+#ifndef HUF_EMU
+    if (huf_b200_device_count() <= 0) return HUF_ERROR_FATAL;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return HUF_ERROR_MEMORY_ALLOCATION;
+    }
+#endif
+    std::lock_guard<std::mutex> lock(g_pinned.mu);
+    g_pinned.v.push_back({static_cast<const uint8_t *>(ptr), bytes});
+    return HUF_ERROR_SUCCESS;
+}
+
+huf_error_t huf_b200_host_unregister(void *ptr)
+{
+    bool known = false;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned.mu);
+        for (size_t i = 0; i < g_pinned.v.size(); i++) {
+            if (g_pinned.v[i].base == ptr) {
+                g_pinned.v.erase(g_pinned.v.begin() + (long)i);
+                known = true;
+                break;
+            }
+        }
+    }
+    if (!known) return HUF_ERROR_INVALID_ARGUMENT;
+#ifndef HUF_EMU
+    if (cudaHostUnregister(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return HUF_ERROR_FATAL;
+    }
+#endif
+    return HUF_ERROR_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
 // host-buffer lanes (see host_pipe.cuh)
 // ------------------------------------------------------------------------------------------
 
@@ -1138,9 +1203,27 @@ huf_error_t huf_b200_encode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
         HUF_TRY_CXX(reserve_device(ps.d_out[i], out_cap));
     }
 
+    // Page-locked caller memory is used in place (huf_b200_host_register): a contiguous source is
+    // read by the H2D copy engine where it lies, a lending sink receives the D2H copy directly;
+    // both save the bounce copy through the lane's own pinned buffers, i.e. half of the host
+    // memory traffic of a call.
+    const bool src_direct = src->data && g_pinned.covers(src->data, src->size);
+    uint8_t *sink_base = nullptr;
+    uint64_t sink_avail = 0, sink_off = 0;
+    bool sink_direct = false;
+    if (dst->room && dst->reserve && dst->commit) {
+        void *p = nullptr;
+        if (dst->room(dst->arg, &p, &sink_avail) == HUF_ERROR_SUCCESS && p && sink_avail >= (64u << 10) &&
+            g_pinned.covers(p, sink_avail)) {
+            sink_base = static_cast<uint8_t *>(p);
+            sink_direct = true;
+        }
+    }
+
     struct Slot {
         uint64_t in_len = 0, out_len = 0;
         bool short_read = false;
+        bool direct = false;  // the result went straight into the sink's buffer
     };
     Slot slots[kSlots];
     Chan<int> free_q, in_q, out_q;
@@ -1169,19 +1252,28 @@ huf_error_t huf_b200_encode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
             const uint64_t want = length - k * span < span ? length - k * span : span;
             uint64_t got = 0;
             const double t0 = now_s();
-            huf_error_t e = source_fill(*src, k * span, ps.pin_in[i].p, want, &got);
-            tm.fill += now_s() - t0;
-            if (e != HUF_ERROR_SUCCESS) {
-                set_fail(e);
-                free_q.push(i);
-                break;
+            const uint8_t *from = ps.pin_in[i].p;
+            if (src_direct) {
+                const uint64_t left = src->size > k * span ? src->size - k * span : 0;
+                got = want < left ? want : left;
+                from = static_cast<const uint8_t *>(src->data) + k * span;
+                g_direct_copies.fetch_add(1);
+            } else {
+                huf_error_t e = source_fill(*src, k * span, ps.pin_in[i].p, want, &got);
+                if (e != HUF_ERROR_SUCCESS) {
+                    set_fail(e);
+                    free_q.push(i);
+                    break;
+                }
             }
+            tm.fill += now_s() - t0;
             taken.fetch_add(got);
             sl.short_read = got < want;
             sl.in_len = sl.short_read ? got / bs * bs : got;  // a short read ends after whole blocks
             sl.out_len = 0;
+            sl.direct = false;
             if (sl.in_len) {
-                cudaMemcpyAsync(ps.d_in[i].p, ps.pin_in[i].p, sl.in_len, cudaMemcpyHostToDevice, ps.s_h2d);
+                cudaMemcpyAsync(ps.d_in[i].p, from, sl.in_len, cudaMemcpyHostToDevice, ps.s_h2d);
                 cudaEventRecord(ps.ev_h2d[i], ps.s_h2d);
             }
             in_q.push(i);
@@ -1205,7 +1297,8 @@ huf_error_t huf_b200_encode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
                 } else {
                     tm.d2h_wait += now_s() - t0;
                     t0 = now_s();
-                    huf_error_t e = sink_deliver(*dst, ps.pin_out[i].p, sl.out_len);
+                    huf_error_t e = sl.direct ? dst->commit(dst->arg, sl.out_len)
+                                              : sink_deliver(*dst, ps.pin_out[i].p, sl.out_len);
                     tm.deliver += now_s() - t0;
                     if (e != HUF_ERROR_SUCCESS) set_fail(e);
                 }
@@ -1235,7 +1328,17 @@ huf_error_t huf_b200_encode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
                     set_fail(e);
                 } else {
                     sl.out_len = n;
-                    cudaMemcpyAsync(ps.pin_out[i].p, ps.d_out[i].p, n, cudaMemcpyDeviceToHost, ps.s_d2h);
+                    // (results leave in span order, so the place of this one in the sink's buffer
+                    // is known; once one does not fit the room that was there at the start the
+                    // rest goes through the bounce buffers, whose delivery may move the buffer)
+                    sl.direct = sink_direct && sink_off + n <= sink_avail;
+                    if (!sl.direct) sink_direct = false;
+                    uint8_t *to = sl.direct ? sink_base + sink_off : ps.pin_out[i].p;
+                    if (sl.direct) {
+                        sink_off += n;
+                        g_direct_copies.fetch_add(1);
+                    }
+                    cudaMemcpyAsync(to, ps.d_out[i].p, n, cudaMemcpyDeviceToHost, ps.s_d2h);
                     cudaEventRecord(ps.ev_d2h[i], ps.s_d2h);
                 }
             }
@@ -1303,8 +1406,23 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
         HUF_TRY_CXX(reserve_pinned(ps.pin_out[i], out_cap));
     }
 
+    // (page-locked caller memory is used in place, see huf_b200_encode_host)
+    const bool src_direct = lent && g_pinned.covers(src->data, src->size);
+    uint8_t *sink_base = nullptr;
+    uint64_t sink_avail = 0, sink_off = 0;
+    bool sink_direct = false;
+    if (dst->room && dst->reserve && dst->commit) {
+        void *p = nullptr;
+        if (dst->room(dst->arg, &p, &sink_avail) == HUF_ERROR_SUCCESS && p && sink_avail >= (64u << 10) &&
+            g_pinned.covers(p, sink_avail)) {
+            sink_base = static_cast<uint8_t *>(p);
+            sink_direct = true;
+        }
+    }
+
     struct Slot {
         uint64_t out_len = 0;
+        bool direct = false;
     };
     Slot slots[kSlots];
     Chan<int> free_q, out_q;
@@ -1346,14 +1464,21 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
             const uint64_t want = planned - at < span ? planned - at : span;
             uint64_t got = 0;
             const double t0 = now_s();
-            huf_error_t e = source_fill(*src, at, ps.pin_in[b].p, want, &got);
-            tm.fill += now_s() - t0;
-            if (e != HUF_ERROR_SUCCESS) {
-                set_fail(e);
-                break;
+            const uint8_t *from = ps.pin_in[b].p;
+            if (src_direct) {
+                got = want;  // (planned = src->size)
+                from = static_cast<const uint8_t *>(src->data) + at;
+                g_direct_copies.fetch_add(1);
+            } else {
+                huf_error_t e = source_fill(*src, at, ps.pin_in[b].p, want, &got);
+                if (e != HUF_ERROR_SUCCESS) {
+                    set_fail(e);
+                    break;
+                }
             }
+            tm.fill += now_s() - t0;
             if (got) {
-                cudaMemcpyAsync(ps.d_stream.p + at, ps.pin_in[b].p, got, cudaMemcpyHostToDevice, ps.s_h2d);
+                cudaMemcpyAsync(ps.d_stream.p + at, from, got, cudaMemcpyHostToDevice, ps.s_h2d);
                 cudaEventRecord(ev[b], ps.s_h2d);
             }
             at += got;
@@ -1381,7 +1506,8 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
                 } else {
                     tm.d2h_wait += now_s() - t0;
                     t0 = now_s();
-                    huf_error_t e = sink_deliver(*dst, ps.pin_out[i].p, slots[i].out_len);
+                    huf_error_t e = slots[i].direct ? dst->commit(dst->arg, slots[i].out_len)
+                                                    : sink_deliver(*dst, ps.pin_out[i].p, slots[i].out_len);
                     tm.deliver += now_s() - t0;
                     if (e != HUF_ERROR_SUCCESS) set_fail(e);
                 }
@@ -1433,8 +1559,16 @@ huf_error_t huf_b200_decode_host(huf_b200_ctx_t *c, const huf_b200_source_t *src
             tm.kern += now_s() - t0;
             npass++;
             slots[i].out_len = n;
+            slots[i].direct = false;
             if (n) {
-                cudaMemcpyAsync(ps.pin_out[i].p, ps.d_out[i].p, n, cudaMemcpyDeviceToHost, ps.s_d2h);
+                slots[i].direct = sink_direct && sink_off + n <= sink_avail;
+                if (!slots[i].direct) sink_direct = false;  // (from here on delivery may move the sink's buffer)
+                uint8_t *to = slots[i].direct ? sink_base + sink_off : ps.pin_out[i].p;
+                if (slots[i].direct) {
+                    sink_off += n;
+                    g_direct_copies.fetch_add(1);
+                }
+                cudaMemcpyAsync(to, ps.d_out[i].p, n, cudaMemcpyDeviceToHost, ps.s_d2h);
                 cudaEventRecord(ps.ev_d2h[i], ps.s_d2h);
             }
             out_q.push(i);  // (also returns an unused slot)

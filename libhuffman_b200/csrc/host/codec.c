@@ -216,6 +216,15 @@ mem_commit(void *arg, uint64_t count)
     return HUF_ERROR_SUCCESS;
 }
 
+static huf_error_t
+mem_room(void *arg, void **dst, uint64_t *avail)
+{
+    mem_sink_t *s = arg;
+    *dst = *s->m->slot ? (uint8_t *)*s->m->slot + s->m->used : NULL;
+    *avail = *s->m->slot ? s->m->room - s->m->used : 0;
+    return HUF_ERROR_SUCCESS;
+}
+
 static void
 make_source(huf_read_writer_t *reader, huf_b200_source_t *src)
 {
@@ -223,6 +232,7 @@ make_source(huf_read_writer_t *reader, huf_b200_source_t *src)
 
     memset(src, 0, sizeof(*src));
     if (m) {
+        huf__memstream_borrow(m);
         src->data = (const uint8_t *)*m->slot + m->rpos;
         src->size = m->used - m->rpos;
         if (!src->data) {
@@ -241,8 +251,10 @@ make_sink(huf_read_writer_t *writer, huf_b200_sink_t *dst, mem_sink_t *ms, uint6
     ms->m = huf__as_memstream(writer);
     ms->expect = expect;
     if (ms->m) {
+        huf__memstream_borrow(ms->m);
         dst->reserve = mem_reserve;
         dst->commit = mem_commit;
+        dst->room = mem_room;
         dst->arg = ms;
     } else {
         dst->push = writer_push;

@@ -19,6 +19,8 @@ typedef struct huf_memstream {
     size_t rpos;   /* read cursor */
     size_t used;   /* bytes written */
     size_t room;   /* allocated bytes */
+    unsigned uses; /* codec calls that borrowed the buffer (huf__memstream_borrow) */
+    void *pinned;  /* the buffer while it is page-locked for direct DMA, else NULL */
 } huf_memstream_t;
 
 /* Returns the memstream behind `rw` when `rw` was created by huf_memopen, else NULL.
@@ -27,6 +29,10 @@ huf_memstream_t *huf__as_memstream(const huf_read_writer_t *rw);
 
 /* Make room for `extra` more bytes at the write end; returns the write pointer. */
 huf_error_t huf__memstream_reserve(huf_memstream_t *m, size_t extra, uint8_t **wptr);
+
+/* A codec call is about to use the stream's buffer in place: counts the use and page-locks a
+ * large buffer that keeps being used (huf_b200_host_register; b200.h says when it pays). */
+void huf__memstream_borrow(huf_memstream_t *m);
 
 /* Read exactly up to `want` bytes by calling rw->read until it reports end of data. */
 huf_error_t huf__read_fully(huf_read_writer_t *rw, void *dst, size_t want, size_t *got);

@@ -11,12 +11,48 @@
  * never ends up smaller than used + count.
  */
 #include <errno.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
 #include "internal.h"
 
 /* ---- memory stream ---------------------------------------------------------------------- */
+
+#define HUF_PIN_MIN_BYTES ((size_t)32 << 20) /* smaller buffers are not worth page-locking */
+
+static void
+mem_unpin(huf_memstream_t *m)
+{
+    if (m->pinned) {
+        (void)huf_b200_host_unregister(m->pinned);
+        m->pinned = NULL;
+    }
+}
+
+void
+huf__memstream_borrow(huf_memstream_t *m)
+{
+    /* HUF_B200_PIN_AFTER: page-lock from this use on (0: never); read per call, it is cheap */
+    const char *env = getenv("HUF_B200_PIN_AFTER");
+    int after = env ? atoi(env) : 4;
+
+    if (after < 0) {
+        after = 0;
+    }
+    size_t floor_bytes = HUF_PIN_MIN_BYTES;
+    if ((env = getenv("HUF_B200_PIN_MIN_BYTES")) != NULL && atoll(env) > 0) {
+        floor_bytes = (size_t)atoll(env); /* (tests) */
+    }
+    m->uses++;
+    if (after && m->uses >= (unsigned)after && !m->pinned && *m->slot && m->room >= floor_bytes) {
+        if (huf_b200_host_register(*m->slot, m->room) == HUF_ERROR_SUCCESS) {
+            m->pinned = *m->slot;
+        } else {
+            m->uses = 0; /* (no GPU, no memory to lock: try again much later, not every call) */
+        }
+    }
+}
 
 huf_error_t
 huf__memstream_reserve(huf_memstream_t *m, size_t extra, uint8_t **wptr)
@@ -34,6 +70,7 @@ huf__memstream_reserve(huf_memstream_t *m, size_t extra, uint8_t **wptr)
         if (m->used) {
             memcpy(fresh, *m->slot, m->used);
         }
+        mem_unpin(m); /* (the next codec call locks the new buffer if the stream is a busy one) */
         free(*m->slot);
         *m->slot = fresh;
         m->room = grown;
@@ -132,6 +169,9 @@ huf_memclose(huf_read_writer_t **self)
 {
     HUF_REQUIRE(self);
     if (*self) {
+        if ((*self)->read == mem_read) {
+            mem_unpin((*self)->stream); /* the caller free()s the buffer: hand it back unlocked */
+        }
         free((*self)->stream); /* the data buffer stays with the caller */
         free(*self);
     }

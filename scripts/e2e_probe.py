@@ -15,7 +15,7 @@ host = datagen.zipf(n, 255, seed=2)
 cap = lib.dll.huf_b200_encode_bound(n, 65536)
 print("THP:", open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip(), flush=True)
 streams = None
-for it in range(4):
+for it in range(8):
     if streams is None or not reuse:
         src = lib.memstream(n); src.write(host)
         mid = lib.memstream(cap); dst = lib.memstream(n)

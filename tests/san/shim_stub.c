@@ -19,3 +19,5 @@ huf_error_t huf_b200_encode_host_multi(huf_b200_ctx_t *const *c, int n, const vo
 huf_error_t huf_b200_decode_host_multi(huf_b200_ctx_t *const *c, int n, const void *h, uint64_t a, uint64_t l,
                                        const huf_b200_sink_t *d, uint64_t *u)
 { (void)c; (void)n; (void)h; (void)a; (void)l; (void)d; (void)u; return HUF_ERROR_FATAL; }
+huf_error_t huf_b200_host_register(void *p, uint64_t n) { (void)p; (void)n; return HUF_ERROR_FATAL; }
+huf_error_t huf_b200_host_unregister(void *p) { (void)p; return HUF_ERROR_SUCCESS; }

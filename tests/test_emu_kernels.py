@@ -479,3 +479,41 @@ def test_emu_encode_pass_pipeline(emu, harness, monkeypatch):
             assert nb == 62 and offs[0] == 0 and offs[-1] == n
         finally:
             codec.close()
+
+
+def test_emu_page_locked_memstreams_are_used_in_place(emu, harness, monkeypatch):
+    """Memory streams that live through several codec calls are page-locked by the library
+    (streams.c huf__memstream_borrow) and the host lanes then copy straight from / into their
+    buffers (huf_b200.cu: src_direct / sink_direct).  Same bytes as the bounce path; a sink that
+    has to grow in the middle of a call falls back and is locked again later; closing releases."""
+    import libhuffman_b200.capi as capi
+    monkeypatch.setenv("HUF_B200_PIN_AFTER", "2")
+    monkeypatch.setenv("HUF_B200_PIN_MIN_BYTES", str(64 << 10))   # (the floor is 32 MiB outside tests)
+    monkeypatch.setenv("HUF_B200_SPAN_BYTES", str(64 << 10))
+    n = (300 << 10) + 777                    # 5 spans
+    data = datagen.zipf(n, 200, seed=9)
+    bs = 8192
+    want = harness.oracle_encode(data, bs)
+    src, mid, dst = emu.memstream(n), emu.memstream(len(want) + 4096), emu.memstream(200 << 10)
+    direct = [emu.dll.huf_b200_direct_copy_count()]
+    try:
+        for it in range(4):
+            for s_ in (src, mid, dst):
+                emu.dll.huf_memrewind(s_.rw)
+            src.write(data)
+            cfg = capi.Config(length=n, blocksize=bs, reader=src.rw, writer=mid.rw)
+            assert emu.dll.huf_encode(C.byref(cfg)) == 0
+            assert C.string_at(mid.buf, len(mid)) == want, it
+            cfg = capi.Config(length=len(mid), reader=mid.rw, writer=dst.rw)
+            assert emu.dll.huf_decode(C.byref(cfg)) == 0
+            # (dst starts too small: it grows inside the first call, is locked from its second use
+            # on, and the calls after that copy straight into it)
+            assert len(dst) == n and C.string_at(dst.buf, n) == data, it
+            direct.append(emu.dll.huf_b200_direct_copy_count())
+        # first call: everything through the bounce buffers; from the second use of a stream on
+        # its buffer is used in place (mid is used twice per round: locked within the first)
+        steps = np.diff(direct)
+        assert steps[0] > 0 and steps[1] > steps[0] and steps[3] == steps[2] >= 3 * 5 + 1, steps
+    finally:
+        for s_ in (src, mid, dst):
+            s_.close()

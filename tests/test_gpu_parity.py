@@ -594,3 +594,38 @@ def test_pipelined_encode_equals_single_stream(lib, harness, torch_cuda, monkeyp
     finally:
         piped.close()
         plain.close()
+
+
+def test_page_locked_memstreams_are_used_in_place(lib, harness, monkeypatch):
+    """Memory streams that live through several codec calls are page-locked by the library and
+    then used in place by the host lanes (no bounce copies: huf_b200.cu src_direct / sink_direct).
+    Same bytes in every round; a sink that grows inside a call falls back and is locked again."""
+    from libhuffman_b200.capi import Config
+    monkeypatch.setenv("HUF_B200_PIN_AFTER", "2")
+    n = (80 << 20) + 12345
+    data = (datagen.zipf(8 << 20, 255, seed=9) * 11)[:n]
+    bs = 65536
+    want = harness.oracle_encode(data[: 4 << 20], bs)
+    src, mid, dst = lib.memstream(n), lib.memstream(lib.dll.huf_b200_encode_bound(n, bs)), lib.memstream(40 << 20)
+    counts = [lib.dll.huf_b200_direct_copy_count()]
+    first = None
+    try:
+        for it in range(4):
+            for s_ in (src, mid, dst):
+                lib.dll.huf_memrewind(s_.rw)
+            src.write(data)
+            cfg = Config(length=n, blocksize=bs, reader=src.rw, writer=mid.rw)
+            assert lib.dll.huf_encode(C.byref(cfg)) == 0
+            stream = C.string_at(mid.buf, len(mid))
+            assert stream[: len(want)] == want          # (the first 4 MiB are whole blocks)
+            first = first or stream
+            assert stream == first, it
+            cfg = Config(length=len(mid), reader=mid.rw, writer=dst.rw)
+            assert lib.dll.huf_decode(C.byref(cfg)) == 0
+            assert len(dst) == n and C.string_at(dst.buf, n) == data, it
+            counts.append(lib.dll.huf_b200_direct_copy_count())
+        steps = np.diff(counts)
+        assert steps[1] > steps[0] and steps[3] == steps[2] >= 3 * 3, steps
+    finally:
+        for s_ in (src, mid, dst):
+            s_.close()
