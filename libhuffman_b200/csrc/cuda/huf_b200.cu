@@ -340,10 +340,7 @@ huf_error_t huf_b200_ctx_destroy(huf_b200_ctx_t **ctx)
         if (c->d_result) cudaFree(c->d_result);
         if (c->h_result) cudaFreeHost(c->h_result);
         if (c->enc_side_ready) {
-            for (int i = 0; i < kEncHistStreams; i++) cudaStreamDestroy(c->enc_hist_st[i]);
-            for (int i = 0; i < kEncBuildStreams; i++) cudaStreamDestroy(c->enc_build_st[i]);
-            for (int i = 0; i < kEncPackStreams; i++) cudaStreamDestroy(c->enc_pack_st[i]);
-            for (int i = 0; i < kEncWideStreams; i++) cudaStreamDestroy(c->enc_wide_st[i]);
+            // (the streams belong to the device's pool, see enc_stream_pool)
             for (int i = 0; i < kEncSlots; i++) {
                 cudaEventDestroy(c->enc_ev_hist[i]);
                 cudaEventDestroy(c->enc_ev_build[i]);
@@ -455,6 +452,45 @@ huf_error_t huf_b200_encode_async(huf_b200_ctx_t *c, const void *d_in, uint64_t 
 }
 
 namespace {
+// The streams of the encoder's pass pipeline: one set per device for the whole process, created
+// once and never destroyed.  (Per context they would be created and destroyed with every codec
+// object; the driver hands its hardware work queues to streams as they are created, and after
+// a few generations the sixteen streams of a context shared queues with each other: the same
+// encode measured 936 and 700 GB/s in two contexts of one process.)
+struct EncStreamPool {
+    bool ready = false;
+    cudaStream_t hist[kEncHistStreams], build[kEncBuildStreams], pack[kEncPackStreams], wide[kEncWideStreams];
+};
+constexpr int kMaxPoolDevices = 64;
+EncStreamPool g_enc_pool[kMaxPoolDevices];
+std::mutex g_enc_pool_mu;
+
+huf_error_t enc_stream_pool(huf_b200_ctx *c)
+{
+    if (c->device < 0 || c->device >= kMaxPoolDevices) return HUF_ERROR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(g_enc_pool_mu);
+    EncStreamPool &p = g_enc_pool[c->device];
+    if (!p.ready) {
+        int prio_lo = 0, prio_hi = 0;  // (numerically: highest priority = smallest value)
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
+        for (int i = 0; i < kEncHistStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&p.hist[i], cudaStreamNonBlocking, prio_lo));
+        for (int i = 0; i < kEncBuildStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&p.build[i], cudaStreamNonBlocking, prio_hi));
+        for (int i = 0; i < kEncPackStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&p.pack[i], cudaStreamNonBlocking, prio_mid));
+        for (int i = 0; i < kEncWideStreams; i++)
+            CU_TRY(cudaStreamCreateWithPriority(&p.wide[i], cudaStreamNonBlocking, prio_mid));
+        p.ready = true;
+    }
+    for (int i = 0; i < kEncHistStreams; i++) c->enc_hist_st[i] = p.hist[i];
+    for (int i = 0; i < kEncBuildStreams; i++) c->enc_build_st[i] = p.build[i];
+    for (int i = 0; i < kEncPackStreams; i++) c->enc_pack_st[i] = p.pack[i];
+    for (int i = 0; i < kEncWideStreams; i++) c->enc_wide_st[i] = p.wide[i];
+    return HUF_ERROR_SUCCESS;
+}
+
 huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length, uint64_t blocksize,
                            void *d_out, uint64_t out_capacity, void *stream)
 {
@@ -515,17 +551,7 @@ huf_error_t encode_enqueue(huf_b200_ctx_t *c, const void *d_in, uint64_t length,
     const uint64_t npasses = (nblocks + per_pass - 1) / per_pass;
     const int nslot = overlap ? (int)(npasses < (uint64_t)c->enc_slots ? npasses : (uint64_t)c->enc_slots) : 1;
     if (overlap && !c->enc_side_ready) {
-        int prio_lo = 0, prio_hi = 0;  // (numerically: highest priority = smallest value)
-        CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
-        for (int i = 0; i < kEncHistStreams; i++)
-            CU_TRY(cudaStreamCreateWithPriority(&c->enc_hist_st[i], cudaStreamNonBlocking, prio_lo));
-        for (int i = 0; i < kEncBuildStreams; i++)
-            CU_TRY(cudaStreamCreateWithPriority(&c->enc_build_st[i], cudaStreamNonBlocking, prio_hi));
-        for (int i = 0; i < kEncPackStreams; i++)
-            CU_TRY(cudaStreamCreateWithPriority(&c->enc_pack_st[i], cudaStreamNonBlocking, prio_mid));
-        for (int i = 0; i < kEncWideStreams; i++)
-            CU_TRY(cudaStreamCreateWithPriority(&c->enc_wide_st[i], cudaStreamNonBlocking, prio_mid));
+        HUF_TRY_CXX(enc_stream_pool(c));
         for (int i = 0; i < kEncSlots; i++) {
             CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_hist[i], cudaEventDisableTiming));
             CU_TRY(cudaEventCreateWithFlags(&c->enc_ev_build[i], cudaEventDisableTiming));

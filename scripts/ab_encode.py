@@ -44,10 +44,10 @@ def run(x, bs, env, no_overlap, reps=10):
 
 
 x = datagen.zipf_torch(n, dev, 255, seed=2)
-for bs in (65536, 4096, 16384, 1 << 20):
+for bs in (65536, 262144, 65536, 262144, 1 << 20, 16384):
     base = run(x, bs, {}, True)
     print(f"bs {bs:8d}  one stream      {base[0]:.3f} ms  {n / base[0] / 1e6:7.1f} GB/s", flush=True)
-    for slots, pass_mib in ((8, 4), (4, 4), (2, 4), (8, 32), (8, 64)):
+    for slots, pass_mib in ((8, 4), (8, 4), (8, 4)):
         env = {"HUF_B200_ENC_SLOTS": str(slots), "HUF_B200_ENC_PIPE_PASS": str(pass_mib << 20)}
         r = run(x, bs, env, False)
         ok = r[1:] == base[1:]
