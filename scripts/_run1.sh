@@ -1,3 +1,5 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --no-header -p no:cacheprovider -k "page_locked or host_lane or length_beyond" 2>&1 | tail -5
-echo "== e2e probe, default (pin after 4)"
-python scripts/e2e_probe.py 1024 reuse 2>&1 | grep -E "iter"
+for cfg in "0 0" "140 0" "144 0" "150 0" "136 1" "144 1"; do
+  set -- $cfg
+  echo "== fill $1 even $2"
+  HUF_B200_DEC_FILL=$1 HUF_B200_DEC_EVEN=$2 python scripts/phase_prof.py run zipf255 1024 2>&1 | grep -E "k_decode|chunks "
+done
