@@ -21,7 +21,7 @@
 
 namespace hufb200 {
 
-constexpr int kMergeDyn = (256 + 16) * 32 * 4;  // one u32 per merge node and lane + the key ring
+constexpr int kMergeDyn = 256 * 32 * 4 + 256 * 32;  // keys / merge nodes (u32) and run lengths (u8) per lane
 
 // ------------------------------------------------------------------------------------------
 // K2a
@@ -92,73 +92,77 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_sort(EncArgs a)
 __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
 {
 #ifdef HUF_EMU
-    uint32_t *nodev = reinterpret_cast<uint32_t *>(hufemu::dyn_smem());
+    uint32_t *arr = reinterpret_cast<uint32_t *>(hufemu::dyn_smem());
 #else
-    extern __shared__ __align__(16) uint32_t nodev[];
+    extern __shared__ __align__(16) uint32_t arr[];
 #endif
-    // nodev[j * 32 + lane] = weight << 8 | (leaves below - 1) of merge node 256 + j
+    // One array of 256 words per lane, transposed (arr[j * 32 + lane]: the bank is the lane's
+    // whatever j each lane is at), serves both queues of the two-queue merge: the sorted leaf
+    // keys sit in it from the start, and merge node 256 + j parks its (weight << 8 | leaves
+    // below - 1) in word j -- free by then: when node j is made, 2 (j + 1) items have been
+    // consumed, at most j of them nodes, so the leaf cursor is already past j + 1.
+    // runlen[j * 32 + lane]: nodes of equal weight from node j on, kept at the first of a run.
     const int lane = lane_id();
     const uint64_t bl = (uint64_t)blockIdx.x * 32 + lane;  // pass-local block
-    if (bl >= a.npass) return;
+    const bool live = bl < a.npass;
     const uint32_t kMax = ~0u;
-    const uint32_t n = a.blk_meta[bl * 4 + 3];
-    const uint32_t *keys = a.blk_keys + bl * 256;  // ascending, n real keys
-    uint2 *out = reinterpret_cast<uint2 *>(a.blk_nodes) + bl * 256;
-    uint32_t *mine = nodev + lane;
-#define NODEV(j) mine[(j) * 32]
-
-    // Leaves are consumed in key order (two keys prefetched).  Merge nodes are created with
-    // non-decreasing weight, so they form runs of equal weight in creation order; the live
-    // ones are [head, top) -- the front run, consumed newest first, its weight in `runw` --
-    // plus [nxt, made).
-    uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0;
-    uint32_t runw = 0;
-    // The keys of a lane's block are a private global array (one sector per lane and load), so
-    // a load issued when its key is needed would put a full memory latency into every step of
-    // the chain.  Keys travel through a per-lane ring in shared memory instead, filled by
-    // asynchronous copies that are issued eight leaf picks before the key is looked at (one
-    // cp.async group per key; absent symbols sort to the end as kMax, so all 256 keys exist).
-    constexpr int kAhead = 8;
-    uint32_t *ring = nodev + 256 * 32 + lane;  // ring[(i & 15) * 32] = keys[i]
-#define KEY(i) ((i) < 256u ? ring[((i) & 15u) * 32] : kMax)
-#pragma unroll
-    for (int i = 0; i < kAhead; i++) {
-        cp_async4(&ring[i * 32], &keys[i]);
-        cp_async_commit();
+    uint32_t *mine = arr + lane;
+    uint8_t *runlen = reinterpret_cast<uint8_t *>(arr + 256 * 32) + lane;
+#define SLOT(j) mine[(j) * 32]
+#define RUNLEN(j) runlen[(j) * 32]
+    // all 256 keys of my block (absent symbols sort to the end as kMax): sixty-four 16-byte loads
+    // in flight together, instead of a load per pick on the chain
+    if (live) {
+        const uint4 *keys = reinterpret_cast<const uint4 *>(a.blk_keys + bl * 256);
+#pragma unroll 8
+        for (int i = 0; i < 64; i++) {
+            const uint4 v = keys[i];
+            SLOT(4 * i) = v.x;
+            SLOT(4 * i + 1) = v.y;
+            SLOT(4 * i + 2) = v.z;
+            SLOT(4 * i + 3) = v.w;
+        }
     }
-    (void)n;
+    __syncwarp();
+    if (!live) return;
+    uint2 *out = reinterpret_cast<uint2 *>(a.blk_nodes) + bl * 256;
+
+    // Leaves are consumed in key order.  Merge nodes are created with non-decreasing weight, so
+    // they form runs of equal weight in creation order; the live ones are [head, top) -- the
+    // front run, consumed newest first, its weight in `runw` -- plus [nxt, made).  A run is
+    // complete before its first node is consumed (what is made afterwards is heavier), so its
+    // length can be kept at its first node and opening a run is two loads, not a scan.
+    uint32_t li = 0, head = 0, top = 0, nxt = 0, made = 0, runw = 0;
+    uint32_t run0 = 0, run_n = 0, last_w = kMax;  // the newest run: first node, length, weight
+    uint32_t k0 = SLOT(0);                          // key of the next leaf (kMax: none left)
     for (;;) {
-        uint32_t pick0 = 0, pick1 = kNone16;
-        uint32_t w0 = 0, w1 = 0, nl = 0;
+        uint32_t pick0 = 0, pick1 = kNone16, w0 = 0, w1 = 0, nl = 0;
         int got = 0;
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             if (top == head && nxt < made) {  // front run used up: open the next one
                 head = nxt;
-                runw = NODEV(nxt) >> 8;
-                uint32_t e = nxt + 1;
-                while (e < made && (NODEV(e) >> 8) == runw) e++;
-                top = nxt = e;
+                runw = SLOT(nxt) >> 8;
+                top = nxt = nxt + RUNLEN(nxt);
             }
             const bool has_i = top > head;
-            const uint32_t ikey = has_i ? make_key<uint32_t>(runw, 255u + top) : kMax;
-            cp_async_wait_group<kAhead - 1>();  // the group of keys[li] has landed
-            const uint32_t k0 = KEY(li);
-            if (ikey == kMax && k0 == kMax) break;  // nothing left (second pick only)
-            uint32_t pick, pw, pl;
-            if (ikey < k0) {
-                top--;
-                pick = 256u + top;
-                pw = runw;
-                pl = (NODEV(top) & 0xffu) + 1u;
-                if (top == head) head = top = nxt;
-            } else {
-                pick = 511u - (k0 & 511u);
-                pw = k0 >> 9;
-                pl = 1;
+            if (!has_i && k0 == kMax) break;  // nothing left (second pick only)
+            // One straight-line pick: the newest node of the front run against the next leaf
+            // (key = weight << 9 | 511 - index: a node beats a leaf of equal weight, a newer node
+            // an older one); both candidates' data are at hand, the winner is selected.
+            const uint32_t ikey = has_i ? ((runw << 9) | (256u - top)) : kMax;
+            const bool node = ikey < k0;
+            const uint32_t nv = SLOT(has_i ? top - 1u : 0u);
+            const uint32_t pick = node ? 255u + top : 511u - (k0 & 511u);
+            const uint32_t pw = node ? runw : (k0 >> 9);
+            const uint32_t pl = node ? (nv & 0xffu) + 1u : 1u;
+            top -= node ? 1u : 0u;
+            const bool spent = node && top == head;
+            head = spent ? nxt : head;
+            top = spent ? nxt : top;
+            if (!node) {
                 li++;
-                if (li + kAhead - 1 < 256u) cp_async4(&ring[((li + kAhead - 1) & 15u) * 32], &keys[li + kAhead - 1]);
-                cp_async_commit();
+                k0 = li < 256u ? SLOT(li) : kMax;
             }
             if (s == 0) {
                 pick0 = pick;
@@ -171,8 +175,14 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
             got++;
         }
         const uint32_t weight = w0 + (got == 2 ? w1 : 0u);
-        NODEV(made) = (weight << 8) | (nl - 1u);
+        SLOT(made) = (weight << 8) | (nl - 1u);
         out[made] = make_uint2(pick0 | (pick1 << 16), nl);
+        // the new node starts a run or extends the newest one
+        const bool same = weight == last_w;
+        run0 = same ? run0 : made;
+        run_n = same ? run_n + 1u : 1u;
+        last_w = weight;
+        RUNLEN(run0) = (uint8_t)run_n;
         // an open front run that is still untouched and is the newest run grows with it
         if (top > head && top == nxt && nxt == made && weight == runw) {
             top++;
@@ -181,8 +191,8 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
         made++;
         if (got < 2) break;
     }
-#undef NODEV
-#undef KEY
+#undef SLOT
+#undef RUNLEN
 }
 
 // ------------------------------------------------------------------------------------------
