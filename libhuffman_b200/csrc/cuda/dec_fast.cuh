@@ -142,12 +142,16 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
         bool ok = active;
         const uint32_t tl = my_tl;
         uint32_t *slot = a.terms + j * kTermStride;
-        // Ancestors whose right slot is still open, one bit per depth: every node opens its
-        // right slot exactly once, so the pending stack is a bit mask and a pop is a clz.
-        // (Eligible trees are at most kLongBits = 32 deep, so mask and path fit 32 bits.)
-        uint32_t pend = 1;            // the root, depth 0
-        uint32_t i = 1, D = 1;        // slot being filled: depth D ...
-        uint32_t C = 0;               // ... reached by the path bits C
+        // The walk fills slots in pre-order; the slot being filled is known by its left-aligned
+        // path bits K and its depth D alone.  A terminal (leaf or absent child) at depth D covers
+        // 2^-D of the code space, so the next open slot starts at K + 2^(32 - D) -- the carry of
+        // that addition runs through the ancestors that were entered to the right and stops at
+        // the deepest one that still has its right slot open, which is exactly where a pre-order
+        // walk continues -- and its depth is the position of the lowest set bit of the sum.  An
+        // inner node just goes one level down to the left (K unchanged).  The tree is complete
+        // when the sum wraps to zero.  (Eligible trees are at most kLongBits = 32 deep.)
+        uint32_t i = 1, D = 1;        // slot being filled: element index, depth ...
+        uint32_t K = 0;               // ... and path bits, left aligned
         uint32_t nterm = 0, min_len = kTreeReach + 1;
         uint32_t wb = 0;              // first element of my staged window
         bool first = true;
@@ -178,43 +182,50 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
             __syncwarp();
 
             if (active) {
-                const uint32_t *hw = reinterpret_cast<const uint32_t *>(hdr + lane * kTreeHdrStride);
+                uint32_t *hw = reinterpret_cast<uint32_t *>(hdr + lane * kTreeHdrStride);
                 const uint32_t skew = (uint32_t)((my_off + kHdrFixed + 2ull * wb) & 3);
-                // Elements i, i+1, i+2 (sign-extended; past tree_len they read as absent
-                // children, src/tree.c:154-160).  The staged words keep the stream's byte skew:
-                // three words and two funnel shifts deliver four consecutive elements.
-                auto elems3 = [&](uint32_t at, int &x0, int &x1, int &x2) {
-                    const uint32_t byte = skew + 2 * (at - wb);
-                    const uint32_t w = byte >> 2, sh = (byte & 3) * 8;
-                    const uint32_t a0 = hw[w], a1 = hw[w + 1], a2 = hw[w + 2];
-                    const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                    x0 = at < tl ? (int)(int16_t)(lo & 0xffffu) : -1;
-                    x1 = at + 1 < tl ? (int)(int16_t)(lo >> 16) : -1;
-                    x2 = at + 2 < tl ? (int)(int16_t)(hi & 0xffffu) : -1;
-                };
-                int e, e1, e2;
+                // The staged words keep the stream's byte skew.  A header at an odd address is
+                // moved down by one byte once, so that every element is an aligned 16-bit word
+                // and the walk reads it with one sign-extending load.
+                if (skew & 1) {
+                    uint32_t lo = hw[0];
+#pragma unroll 8
+                    for (int w = 0; w < kTreeHdrStride / 4 - 1; w++) {
+                        const uint32_t hi = hw[w + 1];
+                        hw[w] = __funnelshift_r(lo, hi, 8);
+                        lo = hi;
+                    }
+                    hw[kTreeHdrStride / 4 - 1] = lo >> 8;
+                }
+                int16_t *el = reinterpret_cast<int16_t *>(hw) + ((skew & 2) >> 1);  // el[k]: element wb + k
+                // elements at and behind tree_len read as absent children (src/tree.c:154-160):
+                // three of them are written behind the last element, and reads are clamped there
+                const uint32_t pad = tl - wb;
+                if (pad <= (uint32_t)kTreeWin) el[pad] = el[pad + 1] = el[pad + 2] = -1;
                 if (first) {
-                    elems3(0, e, e1, e2);
-                    ok = e != -1 && e1 != -1;  // a root with something below its left edge
+                    ok = el[0] != -1 && el[1] != -1;  // a root with something below its left edge
                     first = false;
                 }
                 while (ok) {
                     // elements i .. i+2 must lie in the window (or past the end of the tree)
-                    if (i + 3 > wb + (uint32_t)kTreeWin && wb + (uint32_t)kTreeWin < tl) {
+                    const uint32_t rel = i - wb;
+                    if (rel + 3 > (uint32_t)kTreeWin && wb + (uint32_t)kTreeWin < tl) {
                         wb = i;  // slide the window; the warp reloads it
                         break;
                     }
-                    elems3(i, e, e1, e2);
+                    const uint32_t at = min(rel, pad);
+                    const int e = el[at], e1 = el[at + 1], e2 = el[at + 2];
                     // One straight-line body for the three kinds of slot content (leaf: v, absent,
                     // absent / inner node / absent child): the lanes of a warp sit on different
                     // kinds all the time, so the kinds are selected, not branched on; only the
                     // exits (error, tree complete, window slide) leave the loop.
                     const bool is_abs = e == -1;
-                    const bool is_leaf = !is_abs && e1 == -1 && e2 == -1;
-                    const bool is_inner = !is_abs && !is_leaf;
+                    const bool childless = (e1 & e2) == -1;
+                    const bool is_leaf = !is_abs && childless;
+                    const bool is_inner = !is_abs && !childless;
                     // the right slot of the root must stay empty (table sits behind the root bit);
                     // leaves below an inner node at depth 32 would need more than 32 bits
-                    if ((D == 1 && C == 1 && !is_abs) || (is_inner && D >= (uint32_t)kLongBits)) {
+                    if ((K == 0x80000000u && !is_abs) || (is_inner && D >= (uint32_t)kLongBits)) {
                         ok = false;
                         break;
                     }
@@ -223,36 +234,33 @@ __global__ void __launch_bounds__(32) k_tree(DecArgs a)
                     // exactly at the table depth (long codes); leaves below become records
                     const bool emit_term = in_reach && (!is_inner || D == (uint32_t)kTreeReach);
                     const bool emit_long = is_leaf && !in_reach;
-                    const uint32_t used = nterm + 2 * nlong;
-                    if ((emit_term && used + 2 > (uint32_t)kTermStride) ||
-                        (emit_long && (nlong >= (uint32_t)kLongMax || used + 3 > (uint32_t)kTermStride))) {
-                        ok = false;
-                        break;
-                    }
+                    // (whether the slot can hold everything is decided once, at the end: terminals
+                    // past its capacity pile up on its last word meanwhile; the records cannot
+                    // leave it -- at most (1025 + 32) / 3 leaves -- and what the two lists
+                    // overwrite of each other is never read, such a tree is not eligible)
                     const uint32_t sym = (uint32_t)(e & 0xff);
                     if (emit_term) {
                         const uint32_t entry = is_leaf ? ((sym << 8) | D) : (is_abs ? kFastDead : kFastLong);
-                        slot[nterm++] = ((C << ((uint32_t)kTreeReach - D)) << 16) | entry;
+                        slot[min(nterm, (uint32_t)kTermStride - 1u)] = ((K >> (32 - kTreeReach)) << 16) | entry;
+                        nterm++;
                         if (is_leaf) min_len = min(min_len, D);
                     }
                     if (emit_long) {
-                        slot[kTermStride - 2 * (nlong + 1)] = C << ((uint32_t)kLongBits - D);
+                        slot[kTermStride - 2 * (nlong + 1)] = K;
                         slot[kTermStride - 2 * (nlong + 1) + 1] = (D << 8) | sym;
                         nlong++;
                     }
                     i += is_leaf ? 3u : 1u;
-                    if (!is_inner && pend == 0) {  // every slot filled: the tree is complete
-                        meta = kMetaFast | (min_len << 8) | (nterm << 16);
+                    const uint32_t next = K + (0x80000000u >> (D - 1u));  // behind a terminal at depth D
+                    if (!is_inner && next == 0) {  // every slot filled: the tree is complete
+                        // (one word of the slot stays free, and the records are limited)
+                        if (nterm + 2 * nlong < (uint32_t)kTermStride && nlong <= (uint32_t)kLongMax)
+                            meta = kMetaFast | (min_len << 8) | (nterm << 16);
                         ok = false;
                         break;
                     }
-                    // inner node: its right slot opens, go down to the left; otherwise continue
-                    // in the deepest open right slot (pend != 0 here)
-                    const uint32_t d = 31u - (uint32_t)__clz((int)pend);
-                    const uint32_t c_pop = ((uint32_t)((uint64_t)C >> (D - d)) << 1) | 1u;
-                    pend = is_inner ? (pend | (1u << D)) : (pend & ~(1u << d));
-                    C = is_inner ? (C << 1) : c_pop;
-                    D = is_inner ? D + 1 : d + 1;
+                    D = is_inner ? D + 1u : 33u - (uint32_t)__ffs((int)next);
+                    K = is_inner ? K : next;
                 }
                 if (!ok) active = false;
             }

@@ -27,14 +27,44 @@ constexpr int kMergeDyn = 256 * 32 * 4 + 256 * 32;  // keys / merge nodes (u32) 
 // K2a
 // ------------------------------------------------------------------------------------------
 
+// Compare-exchange network of the bitonic sort, element e = 8 * lane + i held in register i of
+// `lane`: partners at distance j < 8 are registers of the same lane, partners at distance j >= 8
+// the same register of lane ^ (j >> 3), reached by one shuffle.  An element keeps the smaller key
+// of its pair when it is the lower one of an ascending pair or the upper one of a descending pair.
+__device__ __forceinline__ void sort256_in_registers(uint32_t (&key)[8], int lane)
+{
+#pragma unroll
+    for (uint32_t k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 8) {
+                const bool keep_min = ((lane & (j >> 3)) == 0) == ((lane & (k >> 3)) == 0);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t other = __shfl_xor_sync(kFull, key[i], (int)(j >> 3));
+                    key[i] = keep_min ? min(key[i], other) : max(key[i], other);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if ((i & j) == 0) {  // (i, i | j) is a pair; its direction: bit k of the element index
+                        const bool up = k >= 8 ? (lane & (k >> 3)) == 0 : (i & k) == 0;
+                        const uint32_t lo = min(key[i], key[i | j]), hi = max(key[i], key[i | j]);
+                        key[i] = up ? lo : hi;
+                        key[i | j] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBuildWarps * 32) k_build_sort(EncArgs a)
 {
-    __shared__ uint32_t key_all[kBuildWarps][256];
     const int lane = lane_id();
     const uint64_t bl = (uint64_t)blockIdx.x * kBuildWarps + warp_in_cta();  // pass-local block
     if (bl >= a.npass) return;
     const uint64_t b = a.blk0 + bl;
-    uint32_t *key = key_all[warp_in_cta()];
     const uint32_t kMax = ~0u;
 
     const uint64_t blen = blk_len_of(a, b);
@@ -52,36 +82,21 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_sort(EncArgs a)
         cnt[4] += v.z & 0xffffu; cnt[5] += v.z >> 16;
         cnt[6] += v.w & 0xffffu; cnt[7] += v.w >> 16;
     }
+    // keys (absent symbols sort to the end), sorted without leaving the registers: no shared
+    // memory, no barriers, 2 instructions per element and exchange step
+    uint32_t key[8];
     uint32_t present = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t s = lane * 8 + i;
-        key[s] = cnt[i] ? make_key<uint32_t>(cnt[i], s) : kMax;
+        key[i] = cnt[i] ? make_key<uint32_t>(cnt[i], s) : kMax;
         present += cnt[i] != 0;
     }
     const uint32_t n = warp_sum(present);  // distinct symbols, >= 1
-    __syncwarp();
-
-    // bitonic sort of the 256 keys (absent symbols sort to the end)
-    for (uint32_t k = 2; k <= 256; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (uint32_t t = lane; t < 128; t += 32) {
-                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const uint32_t p = i | j;
-                const bool up = (i & k) == 0;
-                const uint32_t x = key[i], y = key[p];
-                if ((x > y) == up) {
-                    key[i] = y;
-                    key[p] = x;
-                }
-            }
-            __syncwarp();
-        }
-    }
-    uint32_t *dst = a.blk_keys + bl * 256;
-#pragma unroll
-    for (int i = 0; i < 8; i++) dst[lane + 32 * i] = key[lane + 32 * i];
+    sort256_in_registers(key, lane);
+    uint4 *dst = reinterpret_cast<uint4 *>(a.blk_keys + bl * 256) + 2 * lane;
+    dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
+    dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
     if (lane == 0) a.blk_meta[bl * 4 + 3] = n;
 }
 
@@ -199,12 +214,21 @@ __global__ void __launch_bounds__(32) k_build_merge(EncArgs a)
 // K2c
 // ------------------------------------------------------------------------------------------
 
+// Code word, length and pre-order position of a node are sums over the edges of its path from the
+// root.  Every merge node keeps a link "I hang `len` edges below merge node `anc`, reached by the
+// path bits `bits`, `pos` elements behind it in the serialised tree"; a round replaces the link by
+// its composition with the link of `anc` (pointer jumping), so after ceil(log2(depth)) rounds every
+// link ends at the root -- a few hundred independent instructions per lane where climbing from
+// every node to the root was a chain of four dependent shared-memory loads per level and node.
 struct CodesSmem {
-    uint16_t isz[256];   // serialised size (elements) of the subtree of merge node 256 + j
-    uint16_t lch[256];
-    uint16_t rch[256];
-    uint16_t par[512];
+    uint64_t bits[256];      // path bits from `anc` down to merge node 256 + j (the low `len` ones)
+    uint32_t link[256];      // anc | len << 16
+    uint16_t pos[256];       // serialised elements between `anc` and the node
+    uint16_t isz[256];       // serialised size (elements) of the subtree of merge node 256 + j
+    uint16_t leaf_up[256];   // symbol s: parent merge node | right child << 15; kNone16: absent
+    uint16_t leaf_pos[256];  // serialised elements between the parent and the leaf
     uint8_t len[256];
+    __align__(16) int16_t tree[kTreeStride];  // the serialised tree, assembled here and copied out in lines
 };
 
 __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(EncArgs a)
@@ -219,28 +243,84 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(EncArgs a)
     const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
     const uint64_t g0 = bl * a.nspb;
     const uint32_t n = a.blk_meta[bl * 4 + 3];  // distinct symbols = merge nodes made
+    const uint32_t root = n - 1;                // the one-child root is the last merge node
 
-    for (int i = lane; i < 512; i += 32) sm.par[i] = kNone16;
-    for (int i = lane; i < 256; i += 32) sm.len[i] = 0;
-    __syncwarp();
     const uint2 *nodes = reinterpret_cast<const uint2 *>(a.blk_nodes) + bl * 256;
-    for (uint32_t j = lane; j < n; j += 32) {
-        const uint2 v = nodes[j];
-        const uint32_t l = v.x & 0xffffu, r = v.x >> 16;
-        sm.lch[j] = (uint16_t)l;
-        sm.rch[j] = (uint16_t)r;
+    uint2 mine[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t j = lane + 32 * i;
+        sm.leaf_up[j] = kNone16;
+        sm.len[j] = 0;
+        mine[i] = j < n ? nodes[j] : make_uint2(0, 0);
         // a subtree with L leaves below a two-child node serialises to 4L - 1 elements; the
         // one-child root adds itself and its absent right child
-        sm.isz[j] = (uint16_t)(r == kNone16 ? 4 * v.y + 1 : 4 * v.y - 1);
-        sm.par[l] = (uint16_t)(256u + j);
-        if (r != kNone16) sm.par[r] = (uint16_t)(256u + j);
+        sm.isz[j] = (uint16_t)((mine[i].x >> 16) == kNone16 ? 4 * mine[i].y + 1 : 4 * mine[i].y - 1);
     }
     __syncwarp();
+    // every merge node hands its children their first link: one edge, to itself
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t j = lane + 32 * i;
+        if (j >= n) continue;
+        const uint32_t l = mine[i].x & 0xffffu, r = mine[i].x >> 16;
+        const uint32_t behind_left = 1u + (l < 256u ? 3u : sm.isz[l - 256u]);
+        if (l < 256u) {
+            sm.leaf_up[l] = (uint16_t)j;
+            sm.leaf_pos[l] = 1;
+        } else {
+            sm.link[l - 256u] = j | (1u << 16);
+            sm.bits[l - 256u] = 0;
+            sm.pos[l - 256u] = 1;
+        }
+        if (r == kNone16) {
+        } else if (r < 256u) {
+            sm.leaf_up[r] = (uint16_t)(j | 0x8000u);
+            sm.leaf_pos[r] = (uint16_t)behind_left;
+        } else {
+            sm.link[r - 256u] = j | (1u << 16);
+            sm.bits[r - 256u] = 1;
+            sm.pos[r - 256u] = (uint16_t)behind_left;
+        }
+        if (j == root) {
+            sm.link[j] = j;  // zero edges below itself: composing with it changes nothing
+            sm.bits[j] = 0;
+            sm.pos[j] = 0;
+        }
+    }
+    __syncwarp();
+    // pointer jumping; links are read by everybody, then written by their owners
+    for (int round = 0; round < 9; round++) {
+        uint32_t up_link[8], up_pos[8];
+        uint64_t up_bits[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t j = lane + 32 * i;
+            const uint32_t anc = j < n ? sm.link[j] & 0xffffu : 0u;
+            up_link[i] = sm.link[anc];
+            up_bits[i] = sm.bits[anc];
+            up_pos[i] = sm.pos[anc];
+        }
+        __syncwarp();
+        bool moving = false;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t j = lane + 32 * i;
+            if (j >= n) continue;
+            const uint32_t len = sm.link[j] >> 16;
+            sm.bits[j] |= len < 64u ? up_bits[i] << len : 0ull;
+            sm.pos[j] = (uint16_t)(sm.pos[j] + up_pos[i]);
+            sm.link[j] = (up_link[i] & 0xffffu) | ((len + (up_link[i] >> 16)) << 16);
+            moving |= (up_link[i] & 0xffffu) != root;
+        }
+        __syncwarp();
+        if (!__any_sync(kFull, moving)) break;
+    }
 
-    // climb from every node to the root: code word + pre-order position
-    const uint32_t root = 255u + n;
-    const uint32_t tree_len = sm.isz[n - 1];
-    int16_t *tree = a.blk_tree + bl * kTreeStride;
+    // (element writes scattered over global memory cost a sector each: the tree is put together
+    // in shared memory and leaves as 16-byte lines)
+    const uint32_t tree_len = sm.isz[root];
+    int16_t *tree = sm.tree;
     uint32_t *tab32 = a.blk_table + bl * 512;
     uint32_t my_max = 0;
     uint64_t code_of[8];
@@ -249,21 +329,13 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(EncArgs a)
     for (int i = 0; i < 8; i++) {
         const uint32_t s = lane + 32 * i;
         uint64_t code = 0;
-        uint32_t len = 0, pos = 0;
-        if (sm.par[s] != kNone16) {
-            uint32_t x = s;
-            while (x != root) {
-                const uint32_t p = sm.par[x];
-                const uint32_t pj = p - 256u;
-                if (sm.rch[pj] == x) {
-                    const uint32_t l = sm.lch[pj];
-                    code |= 1ull << len;
-                    pos += l < 256u ? 3u : sm.isz[l - 256u];
-                }
-                pos += 1;
-                len++;
-                x = p;
-            }
+        uint32_t len = 0;
+        const uint32_t up = sm.leaf_up[s];
+        if (up != kNone16) {
+            const uint32_t pj = up & 0x7fffu;
+            len = (sm.link[pj] >> 16) + 1u;
+            code = (sm.bits[pj] << 1) | (up >> 15);
+            const uint32_t pos = (uint32_t)sm.pos[pj] + sm.leaf_pos[s];
             tree[pos] = (int16_t)s;
             tree[pos + 1] = -1;
             tree[pos + 2] = -1;
@@ -272,22 +344,15 @@ __global__ void __launch_bounds__(kBuildWarps * 32) k_build_codes(EncArgs a)
         code_of[i] = code;
         len_of[i] = len;
         my_max = max(my_max, len);
-    }
-    for (uint32_t v = 256u + lane; v <= root; v += 32) {
-        uint32_t pos = 0, x = v;
-        while (x != root) {
-            const uint32_t p = sm.par[x];
-            const uint32_t pj = p - 256u;
-            if (sm.rch[pj] == x) {
-                const uint32_t l = sm.lch[pj];
-                pos += l < 256u ? 3u : sm.isz[l - 256u];
-            }
-            pos += 1;
-            x = p;
-        }
-        tree[pos] = (int16_t)v;
+        if (s < n) tree[sm.pos[s]] = (int16_t)(256u + s);  // merge node 256 + s
     }
     if (lane == 0) tree[tree_len - 1] = -1;  // absent right child of the one-child root
+    __syncwarp();
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(a.blk_tree + bl * kTreeStride);
+        const uint4 *src = reinterpret_cast<const uint4 *>(sm.tree);
+        for (uint32_t k = lane; 8 * k < tree_len; k += 32) dst[k] = src[k];
+    }
 
     const uint32_t max_len = warp_max(my_max);
     const uint32_t fmt = max_len <= 26 ? 0u : 1u;

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     }
     uint32_t *stage = sm.stage[w];
     const saddr_t stage_s = smem_addr(stage);
+    const saddr_t tab_s = saddr_pin(smem_addr(tab));  // (pinned: otherwise rebuilt from the thread index per iteration)
     __syncwarp();
 
     OutRange r;
@@ -147,7 +148,14 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     // byte.
     const uint64_t gbit = (pay0 << 3) + o;
     uint32_t q = (uint32_t)(gbit & 127);    // bits in front of the cursor inside its line
-    uint64_t wbase = (gbit >> 7) << 2;      // output word index of stage[0] (multiple of 4)
+    // The output word index of stage[0] (a multiple of 4) is kept relative to the owned words
+    // [full_lo, full_hi), in 32 bits: `lead` words until the window starts inside them (at most
+    // 3, never positive again once the first line has left), `room` words from the window to
+    // their end; `line` is where the lane's line of the window goes.
+    const uint64_t wbase0 = (gbit >> 7) << 2;
+    int32_t lead = (int32_t)(r.full_lo - wbase0);
+    int32_t room = (int32_t)(r.full_hi - wbase0);
+    uint4 *line = reinterpret_cast<uint4 *>(r.out) + (wbase0 >> 2) + lane;
     uint32_t carry = 0;                     // unfinished word in front of the cursor (left aligned)
     {
         const uint32_t rb = (uint32_t)(o & 7);
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         for (int j = 0; j < 8; j++) {
             const uint32_t s0 = __byte_perm(sym[j >> 1], 0, 0x4440 + 2 * (j & 1));
             const uint32_t s1 = __byte_perm(sym[j >> 1], 0, 0x4441 + 2 * (j & 1));
-            uint32_t e0 = tab[s0], e1 = tab[s1];
+            uint32_t e0 = lds_u32(tab_s + 4 * s0), e1 = lds_u32(tab_s + 4 * s1);
             if (!FULL) {
                 if ((uint32_t)(2 * j) >= nvalid) e0 = 0;
                 if ((uint32_t)(2 * j + 1) >= nvalid) e1 = 0;
@@ -242,16 +250,21 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         }
         __syncwarp();
 
-        // ---- finished 16-byte lines leave coalesced; the unfinished line stays in front
+        // ---- finished 16-byte lines leave coalesced; the unfinished line stays in front.  An
+        // iteration completes at most (127 + 32 * 16 * 16) / 128 = 64 lines: two per lane.
         const uint32_t nlines = (q + total) >> 7;
-        if (wbase >= r.full_lo && wbase + 4ull * nlines <= r.full_hi) {
+        if (lead <= 0 && (int32_t)(4 * nlines) <= room) {
             // (every iteration but a segment's first and last: all lines lie inside the owned words)
-            uint4 *dst = reinterpret_cast<uint4 *>(r.out) + (wbase >> 2);
-            for (uint32_t L = lane; L < nlines; L += 32) {
-                const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
-                dst[L] = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+            if ((uint32_t)lane < nlines) {
+                const uint4 v = reinterpret_cast<const uint4 *>(stage)[lane];
+                line[0] = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+            }
+            if ((uint32_t)lane + 32 < nlines) {
+                const uint4 v = reinterpret_cast<const uint4 *>(stage)[lane + 32];
+                line[32] = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
             }
         } else {
+            const uint64_t wbase = r.full_hi - (uint64_t)(int64_t)room;
             for (uint32_t L = lane; L < nlines; L += 32) {
                 const uint64_t w0 = wbase + 4 * L;
                 const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
@@ -270,7 +283,9 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         // later words are stored by the lanes that complete them in the next iteration)
         const uint32_t keep = lane < 4 ? stage[4 * nlines + lane] : 0u;
         q = (q + total) & 127;
-        wbase += 4 * nlines;
+        line += nlines;
+        lead -= (int32_t)(4 * nlines);
+        room -= (int32_t)(4 * nlines);
         __syncwarp();
         if (lane < 4) stage[lane] = keep;
         __syncwarp();
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     // which only the owned bytes are written
     if (lane == 0 && (q & 31)) stage[q >> 5] = carry;
     __syncwarp();
-    if (lane < 4 && 32 * (uint32_t)lane < q) store_word(r, wbase + lane, stage[lane]);
+    if (lane < 4 && 32 * (uint32_t)lane < q) store_word(r, r.full_hi - (uint64_t)(int64_t)room + lane, stage[lane]);
 }
 
 }  // namespace hufb200
