@@ -70,7 +70,13 @@ constexpr uint32_t kMetaFast = 1u;
 constexpr int kFT = 128;                  // threads per CTA.  256 threads with sub-blocks half as long (kRegWords 25,
                                           // kMaxSubWords 13) measure within 2-4 % either way: Zipf and Fibonacci
                                           // shapes prefer 128, uniform / text / geometric prefer 256
-constexpr int kRegWords = 51;             // words per thread region (+ one row behind them that
+#ifndef HUF_DEC_REGWORDS
+#define HUF_DEC_REGWORDS 51
+#endif
+#ifndef HUF_DEC_MINCTA
+#define HUF_DEC_MINCTA 4
+#endif
+constexpr int kRegWords = HUF_DEC_REGWORDS;  // words per thread region (+ one row behind them that
                                           // takes the stores of a region that has run full)
 constexpr int kRegCap = 4 * kRegWords;    // symbols a region can hold
 constexpr int kRegRow = kFT * 4;          // regions are interleaved: word c of thread t sits at
@@ -300,7 +306,7 @@ struct FastTail {
 constexpr int kFastSmallOff = kFastTailOff + (int)sizeof(FastTail);
 constexpr int kFastDyn = kFastSmallOff + (int)sizeof(FastSmall);
 static_assert(kFastStage <= kFastLutOff, "the stage must fit in front of the table");
-static_assert(kFastDyn + 1024 <= 233472 / 4, "four CTAs per SM");
+static_assert(kFastDyn + 1024 <= 233472 / HUF_DEC_MINCTA, "CTAs per SM");
 static_assert(sizeof(FastTail) % 8 == 0, "FastSmall holds 64-bit words");
 static_assert(kFastStage % 16 == 0 && kFastRegOff % 16 == 0 && kFastTailOff % 8 == 0, "alignment");
 
@@ -755,7 +761,11 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
         uint32_t warm = 192;
         if (use_guess) {
             const float avg_bits = (float)(guess_end - 8ull * pay0) / (float)orig_len;  // per code word
+            #ifdef HUF_DEC_FILL
+            const float w = (float)kRegCap * HUF_DEC_FILL * avg_bits * (1.0f / 32.0f);
+#else
             const float w = (float)(avg_bits < 5.0f ? kRegCap * 3 / 4 : kRegCap * 2 / 3) * avg_bits * (1.0f / 32.0f);
+#endif
             uint32_t spec = w < (float)kMaxSubWords ? (uint32_t)w : (uint32_t)kMaxSubWords;
             if (!(spec & 1)) spec--;
             if (spec > safe_cap_w && spec <= (uint32_t)kMaxSubWords) sub_cap_w = spec;
@@ -1238,7 +1248,7 @@ __device__ __forceinline__ void decode_fast_body(DecArgs a, uint8_t *dyn)
 
 // The instance every launch uses today: dynamic shared memory starts at shared-window address
 // 0x400 (no static shared memory, 1 KB reserved by the system), which puts the table at 0x4000.
-__global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
+__global__ void __launch_bounds__(kFT, HUF_DEC_MINCTA) k_decode(DecArgs a)
 {
     HUF_DYN_SMEM(dyn);
     decode_fast_body<true>(a, dyn);
@@ -1247,7 +1257,7 @@ __global__ void __launch_bounds__(kFT, 4) k_decode(DecArgs a)
 // Same kernel with the table offset ADDED to its base: launched when the probe finds the table
 // at an address that is not 8 KB aligned (a driver or toolkit that reserves a different amount
 // of shared memory), one more integer instruction per code word.
-__global__ void __launch_bounds__(kFT, 4) k_decode_unaligned(DecArgs a)
+__global__ void __launch_bounds__(kFT, HUF_DEC_MINCTA) k_decode_unaligned(DecArgs a)
 {
     HUF_DYN_SMEM(dyn);
     decode_fast_body<false>(a, dyn);

@@ -31,24 +31,27 @@ struct PackFastSmem {
     __align__(16) uint32_t stage[kEncWarps][kPackStageWords];
 };
 
-// A lane's bit accumulator: `cur` is the word under construction with nb (< 32) bits in it, `at`
-// the shared address it goes to once complete.  A put appends up to 32 bits (t, left aligned;
-// the sum word s carries their number in its low six bits) and stores at most one word.  What
-// does not fit becomes the new word under construction -- and is zero when nothing was stored,
-// so one select replaces the two-register hand-over -- and the byte address advances by itself.
+// A lane's bit accumulator: `cur` is the word under construction, `pos` the lane's running bit
+// position (only its low five bits -- the bits already in cur -- and the carry into bit 5 are
+// looked at, so whatever sits above them rides along: the sum words carry code bits up there),
+// `at` the shared address cur goes to once complete.  A put appends up to 32 bits (t, left
+// aligned; the sum word s carries their number in its low six bits) and stores at most one word:
+// a word boundary was crossed exactly when bit 5 of the position flipped.  What does not fit
+// becomes the new word under construction -- and is zero when nothing was stored, so one select
+// replaces the two-register hand-over -- and the byte address advances by itself.
 struct PackAcc {
-    uint32_t cur, nb;
+    uint32_t cur, pos;
     saddr_t at;
 };
 
 __device__ __forceinline__ void pack_put(PackAcc &s, uint32_t t, uint32_t sum)
 {
-    const uint32_t x = t >> s.nb;                       // (nb < 32)
-    const uint32_t y = __funnelshift_r(0u, t, s.nb);    // t << (32 - nb); 0 for nb == 0
-    const uint32_t n = s.nb + sum;                      // low six bits: bits in cur after the put
+    const uint32_t x = __funnelshift_r(t, 0u, s.pos);   // t >> (pos & 31)
+    const uint32_t y = __funnelshift_r(0u, t, s.pos);   // t << (32 - (pos & 31)); 0 for an empty cur
+    const uint32_t n = s.pos + sum;
     const uint32_t w = s.cur | x;
 #ifdef HUF_EMU
-    const bool full = (n & 32u) != 0;
+    const bool full = ((n ^ s.pos) & 32u) != 0;
     if (full) sts_u32(s.at, w);
     s.cur = full ? y : w;
     s.at += full ? 4u : 0u;
@@ -60,17 +63,18 @@ __device__ __forceinline__ void pack_put(PackAcc &s, uint32_t t, uint32_t sum)
         "{\n\t"
         ".reg .pred p;\n\t"
         ".reg .b32 f;\n\t"
-        "and.b32 f, %3, 32;\n\t"
+        "xor.b32 f, %3, %5;\n\t"
+        "and.b32 f, f, 32;\n\t"
         "setp.ne.u32 p, f, 0;\n\t"
         "@p st.shared.u32 [%1], %2;\n\t"
         "selp.u32 %0, %4, %2, p;\n\t"
         "@p add.u32 %1, %1, 4;\n\t"
         "}"
         : "=r"(s.cur), "+r"(s.at)
-        : "r"(w), "r"(n), "r"(y)
+        : "r"(w), "r"(n), "r"(y), "r"(s.pos)
         : "memory");
 #endif
-    s.nb = n & 31u;
+    s.pos = n;
 }
 
 __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
         if (FULL) {
             PackAcc acc;
             acc.cur = 0;
-            acc.nb = start & 31;
+            acc.pos = start;
             acc.at = stage_s + 4 * first_widx;
 #pragma unroll
             for (int j = 0; j < 8; j++) pack_put(acc, t[j], sp[j]);

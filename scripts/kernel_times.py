@@ -6,6 +6,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 os.environ["HUF_B200_ACCEPT_1025"] = "1"
 import torch
 import libhuffman_b200
+if os.environ.get("HUF_EXP_LIB"):  # an experiment build of the library (scripts/_bin/)
+    libhuffman_b200.LIB_PATH = Path(os.environ["HUF_EXP_LIB"]).resolve()
 from libhuffman_b200 import datagen
 from libhuffman_b200.capi import DeviceCodec
 shape = sys.argv[1]; mib = int(sys.argv[2]) if len(sys.argv) > 2 else 256; bs = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
