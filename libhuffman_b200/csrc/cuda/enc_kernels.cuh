@@ -75,6 +75,46 @@ __device__ __forceinline__ uint64_t blk_len_of(const EncArgs &a, uint64_t b)
     return left < a.blocksize ? left : a.blocksize;
 }
 
+// Block header (reference src/encoder.c:325-342): u64 orig_len | i16 tree_len | i16 tree[tree_len],
+// written by one warp.  The serialised tree is up to 2 KB: the 16-byte lines of the output that hold
+// nothing but tree elements are assembled from aligned words of the workspace copy (shifted to the
+// header's byte alignment, which is arbitrary) and stored whole; only the bytes around them -- the
+// ten fixed ones, the ragged head and tail of the tree -- go byte by byte.
+__device__ __forceinline__ void emit_block_header(const EncArgs &a, uint64_t bl, uint64_t blen, uint32_t tree_len,
+                                                  uint64_t boff, int lane)
+{
+    const int16_t *tree = a.blk_tree + bl * kTreeStride;
+    const uint32_t *tw = reinterpret_cast<const uint32_t *>(tree);
+    const uint32_t hlen = kHdrFixed + 2 * tree_len;
+    uint8_t *dst = a.out + boff;
+    // header bytes [i0, i1): whole output lines made of tree bytes only
+    uint32_t i0 = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15)) & 15u;
+    if (i0 < (uint32_t)kHdrFixed) i0 += 16;
+    if (i0 > hlen) i0 = hlen;
+    const uint32_t i1 = i0 + ((hlen - i0) & ~15u);
+    for (uint32_t i = i0 + 16 * lane; i < i1; i += 512) {
+        const uint32_t t0 = i - kHdrFixed;  // byte offset into the serialised tree
+        const uint32_t *w = tw + (t0 >> 2);
+        const uint32_t sh = (t0 & 3) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        *reinterpret_cast<uint4 *>(dst + i) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                                         __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+    const uint32_t around = i0 + (hlen - i1);
+    for (uint32_t e = lane; e < around; e += 32) {
+        const uint32_t i = e < i0 ? e : e - i0 + i1;
+        uint32_t v;
+        if (i < 8) {
+            v = (uint32_t)(blen >> (8 * i));
+        } else if (i < 10) {
+            v = tree_len >> (8 * (i - 8));
+        } else {
+            v = (uint32_t)(uint16_t)tree[(i - 10) >> 1] >> (8 * (i & 1));
+        }
+        dst[i] = (uint8_t)v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: per-segment byte histogram.
 // ------------------------------------------------------------------------------------------
@@ -568,22 +608,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack_wide(EncArgs a)
     const uint64_t o_end = last_seg ? bits_total : a.seg_bitoff[g + 1];
 
     // block header: written by the warp that owns segment 0
-    if (k == 0) {
-        const int16_t *tree = a.blk_tree + bl * kTreeStride;
-        const uint32_t hlen = kHdrFixed + 2 * tree_len;
-        uint8_t *dst = a.out + boff;
-        for (uint32_t i = lane; i < hlen; i += 32) {
-            uint32_t v;
-            if (i < 8) {
-                v = (uint32_t)(blen >> (8 * i));
-            } else if (i < 10) {
-                v = tree_len >> (8 * (i - 8));
-            } else {
-                v = (uint32_t)(uint16_t)tree[(i - 10) >> 1] >> (8 * (i & 1));
-            }
-            dst[i] = (uint8_t)v;
-        }
-    }
+    if (k == 0) emit_block_header(a, bl, blen, tree_len, boff, lane);
 
     // per-warp copy of the code table
     uint32_t *tab = sm.table[w];

@@ -108,22 +108,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     const uint64_t o_end = last_seg ? bits_total : a.seg_bitoff[g + 1];
 
     // block header: written by the warp that owns segment 0
-    if (k == 0) {
-        const int16_t *tree = a.blk_tree + bl * kTreeStride;
-        const uint32_t hlen = kHdrFixed + 2 * tree_len;
-        uint8_t *dst = a.out + boff;
-        for (uint32_t i = lane; i < hlen; i += 32) {
-            uint32_t v;
-            if (i < 8) {
-                v = (uint32_t)(blen >> (8 * i));
-            } else if (i < 10) {
-                v = tree_len >> (8 * (i - 8));
-            } else {
-                v = (uint32_t)(uint16_t)tree[(i - 10) >> 1] >> (8 * (i & 1));
-            }
-            dst[i] = (uint8_t)v;
-        }
-    }
+    if (k == 0) emit_block_header(a, bl, blen, tree_len, boff, lane);
 
     // per-warp copy of the code table (codes are at most 16 bits here: the low half holds the length)
     uint32_t *tab = sm.table[w];
