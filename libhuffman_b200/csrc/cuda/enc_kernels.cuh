@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_sizes(const uint64_t *__r
 // K3: bit packing.
 // ------------------------------------------------------------------------------------------
 
-constexpr int kStageWords = 424;  // 512 symbols * 26 bits / 32 + slack
+constexpr int kStageWords = 912;  // 512 symbols * 56 bits / 32 + the kept line + slack
 
 struct PackSmem {
     uint32_t table[kEncWarps][512];       // per-warp copy of the block's code table
@@ -569,186 +569,7 @@ __device__ __forceinline__ uint32_t pack_flush_carry(const BitAcc &acc, uint32_t
     return out;
 }
 
-// General lane of K3: blocks whose longest code word exceeds kPackWideMinLen - 1 bits, and blocks
-// of a single symbol (the fast lane in enc_pack.cuh takes all others); status[2] counts them.
-constexpr uint32_t kPackWideMinLen = 17;
-
-__global__ void __launch_bounds__(kEncWarps * 32) k_pack_wide(EncArgs a)
-{
-    __shared__ PackSmem sm;
-    const int lane = lane_id();
-    const int w = warp_in_cta();
-    const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
-    if (g >= a.npass * a.nspb) return;
-    if (a.status[0] != kOk) return;
-    if (a.status[2] == 0) return;  // no deep block in this call
-
-    const uint64_t bl = g / a.nspb;
-    // (blocks of one symbol have a 1-bit code: sixteen symbols of a lane do not fill a word, which
-    // the fast lane's hand-over between neighbouring lanes relies on)
-    if (a.blk_meta[bl * 4 + 1] < kPackWideMinLen && a.blk_meta[bl * 4 + 3] != 1) return;
-    const uint64_t b = a.blk0 + bl;
-    const uint32_t k = (uint32_t)(g % a.nspb);
-    const uint64_t blen = blk_len_of(a, b);
-    const uint64_t soff = (uint64_t)k * a.seg;
-    if (soff >= blen) return;
-    const uint32_t slen = (uint32_t)((blen - soff) < a.seg ? (blen - soff) : a.seg);
-    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
-    const uint8_t *blk_in = a.in + b * a.blocksize;
-    const uint8_t *p = blk_in + soff;
-
-    const uint32_t *meta = a.blk_meta + bl * 4;
-    const uint32_t tree_len = meta[0];
-    const uint32_t fmt = meta[2];
-    const uint64_t boff = a.blk_off[b];
-    const uint64_t pay0 = boff + kHdrFixed + 2ull * tree_len;  // first payload byte
-    const uint64_t bits_total = a.blk_bits[bl];
-    const uint64_t o = a.seg_bitoff[g];
-    const bool last_seg = (k + 1 == nseg_b);
-    const uint64_t o_end = last_seg ? bits_total : a.seg_bitoff[g + 1];
-
-    // block header: written by the warp that owns segment 0
-    if (k == 0) emit_block_header(a, bl, blen, tree_len, boff, lane);
-
-    // per-warp copy of the code table
-    uint32_t *tab = sm.table[w];
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.blk_table + bl * 512);
-        uint4 *dst = reinterpret_cast<uint4 *>(tab);
-        const int n16 = fmt == 0 ? 64 : 128;
-        for (int i = lane; i < n16; i += 32) dst[i] = src[i];
-    }
-    __syncwarp();
-
-    OutRange r;
-    r.out = a.out;
-    r.b0 = pay0 + (o >> 3);
-    r.b1 = last_seg ? pay0 + ((bits_total + 7) >> 3) : pay0 + (o_end >> 3);
-    r.full_lo = (r.b0 + 3) >> 2;
-    r.full_hi = r.b1 >> 2;
-
-    // Global bit cursor.  The first byte of the segment may begin with the last bits of the
-    // previous segment's final code words: rebuild them so this warp owns the whole byte.
-    uint64_t gbit = (pay0 << 3) + o;
-    uint32_t q = (uint32_t)(gbit & 31);
-    uint64_t wbase = gbit >> 5;
-    uint32_t carry = 0;
-    {
-        const uint32_t rb = (uint32_t)(o & 7);
-        if (rb) {
-            uint32_t val = 0;
-            if (lane == 0) {
-                uint32_t got = 0;
-                uint64_t idx = soff;
-                while (got < rb) {
-                    idx--;
-                    const uint32_t s = blk_in[idx];
-                    uint32_t c, l;
-                    if (fmt == 0) {
-                        const uint32_t e = tab[s];
-                        l = e & 31u;
-                        c = (e & ~31u) >> (32 - l);
-                    } else {
-                        const uint64_t e = reinterpret_cast<const uint64_t *>(tab)[s];
-                        l = (uint32_t)(e & 0xffu);
-                        c = (uint32_t)((e & ~0xffull) >> (64 - l));  // low bits suffice
-                    }
-                    val |= c << got;
-                    got += l;
-                }
-                val &= (1u << rb) - 1u;
-            }
-            val = __shfl_sync(kFull, val, 0);
-            carry = val << (32 - q);
-        }
-    }
-
-    uint32_t *stage = sm.stage[w];
-    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
-    const int per_lane = fmt == 0 ? 16 : 4;              // symbols per lane per iteration
-    const uint32_t step = 32u * per_lane;
-
-    for (uint32_t base = 0; base < slen; base += step) {
-        // ---- load this lane's symbols
-        const uint32_t my0 = base + lane * per_lane;
-        uint32_t sym[4] = {0, 0, 0, 0};  // 16 bytes, little endian in words
-        uint32_t nvalid = 0;
-        if (my0 < slen) nvalid = min((uint32_t)per_lane, slen - my0);
-        if (per_lane == 16 && aligned && nvalid == 16) {
-            const uint4 v = ld_stream_u4(p + my0);
-            sym[0] = v.x; sym[1] = v.y; sym[2] = v.z; sym[3] = v.w;
-        } else {
-            // ragged tail / unaligned input: byte loads, static register indices
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if ((uint32_t)j < nvalid) sym[j >> 2] |= (uint32_t)p[my0 + j] << (8 * (j & 3));
-            }
-        }
-
-        uint32_t total_l = 0;
-        BitAcc acc;
-        if (fmt == 0) {
-            // ---- look up code words, sum the lengths
-            uint32_t e[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t s = (sym[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                e[j] = (uint32_t)j < nvalid ? tab[s] : 0u;
-                total_l += e[j] & 31u;
-            }
-            const uint32_t incl = warp_incl_scan(total_l);
-            const uint32_t total = __shfl_sync(kFull, incl, 31);
-            const uint32_t start = q + incl - total_l;
-            acc.hi = acc.lo = 0;
-            acc.nb = start & 31;
-            acc.widx = start >> 5;
-            const uint32_t first_widx = acc.widx;
-#pragma unroll
-            for (int j = 0; j < 16; j++) acc_put(acc, stage, e[j] & ~31u, e[j] & 31u);
-            carry = pack_flush_carry(acc, first_widx, stage, carry);
-            __syncwarp();
-
-            // ---- copy finished words out, coalesced
-            const uint32_t nfull = (q + total) >> 5;
-            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
-            q = (q + total) & 31;
-            wbase += nfull;
-            __syncwarp();
-        } else {
-            uint64_t e[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t s = (sym[0] >> (8 * j)) & 0xffu;
-                e[j] = (uint32_t)j < nvalid ? reinterpret_cast<const uint64_t *>(tab)[s] : 0ull;
-                total_l += (uint32_t)(e[j] & 0xffu);
-            }
-            const uint32_t incl = warp_incl_scan(total_l);
-            const uint32_t total = __shfl_sync(kFull, incl, 31);
-            const uint32_t start = q + incl - total_l;
-            acc.hi = acc.lo = 0;
-            acc.nb = start & 31;
-            acc.widx = start >> 5;
-            const uint32_t first_widx = acc.widx;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t l = (uint32_t)(e[j] & 0xffu);
-                const uint64_t t = e[j] & ~0xffull;
-                const uint32_t l1 = min(l, 32u);
-                acc_put(acc, stage, (uint32_t)(t >> 32), l1);
-                acc_put(acc, stage, (uint32_t)t, l - l1);
-            }
-            carry = pack_flush_carry(acc, first_widx, stage, carry);
-            __syncwarp();
-
-            const uint32_t nfull = (q + total) >> 5;
-            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
-            q = (q + total) & 31;
-            wbase += nfull;
-            __syncwarp();
-        }
-    }
-    // trailing partial word: only its owned bytes are written
-    if (q && lane == 0) store_word(r, wbase, carry);
-}
+// (k_pack_wide, the general lane of K3, lives in enc_pack.cuh behind the fast lane whose
+// accumulator it shares)
 
 }  // namespace hufb200

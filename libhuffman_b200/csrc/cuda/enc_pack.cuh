@@ -293,4 +293,282 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
     if (lane < 4 && 32 * (uint32_t)lane < q) store_word(r, r.full_hi - (uint64_t)(int64_t)room + lane, stage[lane]);
 }
 
+// General lane of K3: blocks whose longest code word exceeds kPackWideMinLen - 1 bits, and blocks
+// of a single symbol (the fast lane in enc_pack.cuh takes all others); status[2] counts them.
+constexpr uint32_t kPackWideMinLen = 17;
+
+__global__ void __launch_bounds__(kEncWarps * 32) k_pack_wide(EncArgs a)
+{
+    __shared__ PackSmem sm;
+    const int lane = lane_id();
+    const int w = warp_in_cta();
+    const uint64_t g = (uint64_t)blockIdx.x * kEncWarps + w;  // pass-local segment index
+    if (g >= a.npass * a.nspb) return;
+    if (a.status[0] != kOk) return;
+    if (a.status[2] == 0) return;  // no deep block in this call
+
+    const uint64_t bl = g / a.nspb;
+    // (blocks of one symbol have a 1-bit code: sixteen symbols of a lane do not fill a word, which
+    // the fast lane's hand-over between neighbouring lanes relies on)
+    if (a.blk_meta[bl * 4 + 1] < kPackWideMinLen && a.blk_meta[bl * 4 + 3] != 1) return;
+    const uint64_t b = a.blk0 + bl;
+    const uint32_t k = (uint32_t)(g % a.nspb);
+    const uint64_t blen = blk_len_of(a, b);
+    const uint64_t soff = (uint64_t)k * a.seg;
+    if (soff >= blen) return;
+    const uint32_t slen = (uint32_t)((blen - soff) < a.seg ? (blen - soff) : a.seg);
+    const uint32_t nseg_b = (uint32_t)((blen + a.seg - 1) / a.seg);
+    const uint8_t *blk_in = a.in + b * a.blocksize;
+    const uint8_t *p = blk_in + soff;
+
+    const uint32_t *meta = a.blk_meta + bl * 4;
+    const uint32_t tree_len = meta[0];
+    const uint32_t fmt = meta[2];
+    const uint64_t boff = a.blk_off[b];
+    const uint64_t pay0 = boff + kHdrFixed + 2ull * tree_len;  // first payload byte
+    const uint64_t bits_total = a.blk_bits[bl];
+    const uint64_t o = a.seg_bitoff[g];
+    const bool last_seg = (k + 1 == nseg_b);
+    const uint64_t o_end = last_seg ? bits_total : a.seg_bitoff[g + 1];
+
+    // block header: written by the warp that owns segment 0
+    if (k == 0) emit_block_header(a, bl, blen, tree_len, boff, lane);
+
+    // per-warp copy of the code table
+    uint32_t *tab = sm.table[w];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.blk_table + bl * 512);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        const int n16 = fmt == 0 ? 64 : 128;
+        for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+
+    OutRange r;
+    r.out = a.out;
+    r.b0 = pay0 + (o >> 3);
+    r.b1 = last_seg ? pay0 + ((bits_total + 7) >> 3) : pay0 + (o_end >> 3);
+    r.full_lo = (r.b0 + 3) >> 2;
+    r.full_hi = r.b1 >> 2;
+
+    // Global bit cursor.  The first byte of the segment may begin with the last bits of the
+    // previous segment's final code words: rebuild them so this warp owns the whole byte.
+    uint64_t gbit = (pay0 << 3) + o;
+    uint32_t q = (uint32_t)(gbit & 31);
+    uint64_t wbase = gbit >> 5;
+    uint32_t carry = 0;
+    {
+        const uint32_t rb = (uint32_t)(o & 7);
+        if (rb) {
+            uint32_t val = 0;
+            if (lane == 0) {
+                uint32_t got = 0;
+                uint64_t idx = soff;
+                while (got < rb) {
+                    idx--;
+                    const uint32_t s = blk_in[idx];
+                    uint32_t c, l;
+                    if (fmt == 0) {
+                        const uint32_t e = tab[s];
+                        l = e & 31u;
+                        c = (e & ~31u) >> (32 - l);
+                    } else {
+                        const uint64_t e = reinterpret_cast<const uint64_t *>(tab)[s];
+                        l = (uint32_t)(e & 0xffu);
+                        c = (uint32_t)((e & ~0xffull) >> (64 - l));  // low bits suffice
+                    }
+                    val |= c << got;
+                    got += l;
+                }
+                val &= (1u << rb) - 1u;
+            }
+            val = __shfl_sync(kFull, val, 0);
+            carry = val << (32 - q);
+        }
+    }
+
+    uint32_t *stage = sm.stage[w];
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    const int per_lane = fmt == 0 ? 16 : 4;              // symbols per lane per iteration
+    const uint32_t step = 32u * per_lane;
+    uint32_t base = 0;
+
+    // Whole rows of 512 symbols go the way of the fast lane (enc_pack.cuh: 16 symbols per lane,
+    // one-word accumulator keyed by the running bit position, completed words stored plainly,
+    // leftovers handed to the right neighbour, 16-byte line stores) with one put per code word
+    // of up to 26 bits, two per code word of up to 56: every code word of such a block has at
+    // least two bits, so every lane completes a word per row.  The ragged end of a segment,
+    // unaligned buffers and one-symbol blocks (1-bit code words) take the general loop below.
+    if (aligned && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && meta[3] != 1 && slen >= 512) {
+        uint32_t ql = (uint32_t)(gbit & 127);  // bits in front of the cursor inside its 16-byte line
+        const uint64_t wbase0 = (gbit >> 7) << 2;
+        int32_t lead = (int32_t)(r.full_lo - wbase0);
+        int32_t room = (int32_t)(r.full_hi - wbase0);
+        uint4 *line = reinterpret_cast<uint4 *>(r.out) + (wbase0 >> 2) + lane;
+        const saddr_t stage_s = smem_addr(stage);
+        const saddr_t tab_s = saddr_pin(smem_addr(tab));
+        if (lane < 4) stage[lane] = 0;  // (words of the first line in front of the cursor: not ours, never output)
+        __syncwarp();
+        uint4 pre = ld_stream_u4(p + lane * 16);
+        auto row = [&](auto wide_tag) {
+            constexpr bool WIDE = decltype(wide_tag)::value;  // 64-bit table entries
+            const uint32_t sym[4] = {pre.x, pre.y, pre.z, pre.w};
+            if (base + 1024 <= slen) pre = ld_stream_u4(p + base + 512 + lane * 16);
+            uint32_t hi[16], lo[WIDE ? 16 : 1], total_l = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t s = __byte_perm(sym[j >> 2], 0, 0x4440 + (j & 3));
+                if constexpr (WIDE) {
+                    lds_u32x2(tab_s + 8 * s, lo[j], hi[j]);
+                    total_l += lo[j] & 0xffu;
+                } else {
+                    hi[j] = lds_u32(tab_s + 4 * s);
+                    total_l += hi[j] & 31u;
+                }
+            }
+            const uint32_t incl = warp_incl_scan(total_l);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            const uint32_t start = ql + incl - total_l;
+            const uint32_t first_widx = start >> 5;
+            PackAcc acc;
+            acc.cur = 0;
+            acc.pos = start;
+            acc.at = stage_s + 4 * first_widx;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if constexpr (WIDE) {
+                    const uint32_t l = lo[j] & 0xffu;
+                    const uint32_t l1 = min(l, 32u);
+                    pack_put(acc, hi[j], l1);
+                    pack_put(acc, lo[j] & ~0xffu, l - l1);
+                } else {
+                    pack_put(acc, hi[j] & ~31u, hi[j] & 31u);
+                }
+            }
+            uint32_t in = __shfl_up_sync(kFull, acc.cur, 1);
+            if (lane == 0) in = carry;
+            carry = __shfl_sync(kFull, acc.cur, 31);
+            stage[first_widx] |= in;
+            __syncwarp();
+            const uint32_t nlines = (ql + total) >> 7;
+            if (lead <= 0 && (int32_t)(4 * nlines) <= room) {
+                for (uint32_t L = lane; L < nlines; L += 32) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
+                    line[L - lane] = make_uint4(bswap32(v.x), bswap32(v.y), bswap32(v.z), bswap32(v.w));
+                }
+            } else {
+                const uint64_t wline = r.full_hi - (uint64_t)(int64_t)room;
+                for (uint32_t L = lane; L < nlines; L += 32) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(stage)[L];
+                    store_word(r, wline + 4 * L, v.x);
+                    store_word(r, wline + 4 * L + 1, v.y);
+                    store_word(r, wline + 4 * L + 2, v.z);
+                    store_word(r, wline + 4 * L + 3, v.w);
+                }
+            }
+            const uint32_t keep = lane < 4 ? stage[4 * nlines + lane] : 0u;
+            ql = (ql + total) & 127;
+            line += nlines;
+            lead -= (int32_t)(4 * nlines);
+            room -= (int32_t)(4 * nlines);
+            __syncwarp();
+            if (lane < 4) stage[lane] = keep;
+            __syncwarp();
+        };
+        if (fmt == 0) {
+            for (; base + 512 <= slen; base += 512) row(std::false_type{});
+        } else {
+            for (; base + 512 <= slen; base += 512) row(std::true_type{});
+        }
+        // back to the word cursor of the general loop: the complete words of the unfinished line leave now
+        const uint64_t wline = r.full_hi - (uint64_t)(int64_t)room;
+        if ((uint32_t)lane < (ql >> 5)) store_word(r, wline + lane, stage[lane]);
+        __syncwarp();
+        q = ql & 31;
+        wbase = wline + (ql >> 5);
+    }
+
+    for (; base < slen; base += step) {
+        // ---- load this lane's symbols
+        const uint32_t my0 = base + lane * per_lane;
+        uint32_t sym[4] = {0, 0, 0, 0};  // 16 bytes, little endian in words
+        uint32_t nvalid = 0;
+        if (my0 < slen) nvalid = min((uint32_t)per_lane, slen - my0);
+        if (per_lane == 16 && aligned && nvalid == 16) {
+            const uint4 v = ld_stream_u4(p + my0);
+            sym[0] = v.x; sym[1] = v.y; sym[2] = v.z; sym[3] = v.w;
+        } else {
+            // ragged tail / unaligned input: byte loads, static register indices
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((uint32_t)j < nvalid) sym[j >> 2] |= (uint32_t)p[my0 + j] << (8 * (j & 3));
+            }
+        }
+
+        uint32_t total_l = 0;
+        BitAcc acc;
+        if (fmt == 0) {
+            // ---- look up code words, sum the lengths
+            uint32_t e[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t s = (sym[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                e[j] = (uint32_t)j < nvalid ? tab[s] : 0u;
+                total_l += e[j] & 31u;
+            }
+            const uint32_t incl = warp_incl_scan(total_l);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            const uint32_t start = q + incl - total_l;
+            acc.hi = acc.lo = 0;
+            acc.nb = start & 31;
+            acc.widx = start >> 5;
+            const uint32_t first_widx = acc.widx;
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc_put(acc, stage, e[j] & ~31u, e[j] & 31u);
+            carry = pack_flush_carry(acc, first_widx, stage, carry);
+            __syncwarp();
+
+            // ---- copy finished words out, coalesced
+            const uint32_t nfull = (q + total) >> 5;
+            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
+            q = (q + total) & 31;
+            wbase += nfull;
+            __syncwarp();
+        } else {
+            uint64_t e[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t s = (sym[0] >> (8 * j)) & 0xffu;
+                e[j] = (uint32_t)j < nvalid ? reinterpret_cast<const uint64_t *>(tab)[s] : 0ull;
+                total_l += (uint32_t)(e[j] & 0xffu);
+            }
+            const uint32_t incl = warp_incl_scan(total_l);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            const uint32_t start = q + incl - total_l;
+            acc.hi = acc.lo = 0;
+            acc.nb = start & 31;
+            acc.widx = start >> 5;
+            const uint32_t first_widx = acc.widx;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t l = (uint32_t)(e[j] & 0xffu);
+                const uint64_t t = e[j] & ~0xffull;
+                const uint32_t l1 = min(l, 32u);
+                acc_put(acc, stage, (uint32_t)(t >> 32), l1);
+                acc_put(acc, stage, (uint32_t)t, l - l1);
+            }
+            carry = pack_flush_carry(acc, first_widx, stage, carry);
+            __syncwarp();
+
+            const uint32_t nfull = (q + total) >> 5;
+            for (uint32_t i = lane; i < nfull; i += 32) store_word(r, wbase + i, stage[i]);
+            q = (q + total) & 31;
+            wbase += nfull;
+            __syncwarp();
+        }
+    }
+    // trailing partial word: only its owned bytes are written
+    if (q && lane == 0) store_word(r, wbase, carry);
+}
+
 }  // namespace hufb200

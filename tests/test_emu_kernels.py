@@ -517,3 +517,15 @@ def test_emu_page_locked_memstreams_are_used_in_place(emu, harness, monkeypatch)
     finally:
         for s_ in (src, mid, dst):
             s_.close()
+
+
+@pytest.mark.parametrize("blocksize,extra", [(1 << 18, 4097), (1 << 20, 70001)])
+def test_emu_general_packing_lane_whole_rows(emu, harness, blocksize, extra):
+    """k_pack_wide packs whole rows of 512 symbols the way the fast lane does (one put per code
+    word of up to 26 bits: Fibonacci counts in 256 KiB give 25-bit code words; two puts per code
+    word of up to 56 bits: 1 MiB gives 28 bits) and hands the ragged end of a segment to its
+    general loop; the second block is short and ends inside a row."""
+    data = datagen.fibonacci_block(blocksize, seed=6) + datagen.fibonacci_block(extra, seed=7)
+    rc, got = emu.encode(data, blocksize)
+    assert rc == 0
+    assert got == harness.oracle_encode(data, blocksize)
