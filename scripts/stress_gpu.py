@@ -21,7 +21,11 @@ shapes = {
     "uniform": lambda: datagen.uniform(n, 256, seed=3),
     "fibonacci": lambda: datagen.fibonacci(n, 65536, seed=4),
     "geometric": lambda: datagen.geometric(n, seed=4),
+    # 1 MiB Fibonacci blocks: 28-bit code words, the 64-bit table entries of the general packing lane
+    "fib1m": lambda: datagen.fibonacci(max(n, 1 << 20) + 70001, 1 << 20, seed=5),
 }
+if os.environ.get("HUF_STRESS_SHAPES"):  # a comma-separated subset (sanitizer runs on a budget)
+    shapes = {k: v for k, v in shapes.items() if k in os.environ["HUF_STRESS_SHAPES"].split(",")}
 bad = 0
 for name, gen in shapes.items():
     data = gen()
