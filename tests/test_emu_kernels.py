@@ -529,3 +529,24 @@ def test_emu_general_packing_lane_whole_rows(emu, harness, blocksize, extra):
     rc, got = emu.encode(data, blocksize)
     assert rc == 0
     assert got == harness.oracle_encode(data, blocksize)
+
+
+def test_emu_block_headers_at_every_alignment(emu, harness):
+    """The block header leaves in 16-byte lines assembled from the workspace copy of the tree and
+    shifted to the header's byte alignment (emit_block_header): blocks of varying length and
+    alphabet put headers of 21 ... 2060 bytes at every residue modulo 16."""
+    rng = np.random.default_rng(11)
+    parts, bs = [], 2500
+    for i in range(48):
+        nsym = int(rng.integers(2, 257))
+        parts.append(rng.integers(0, nsym, size=bs, dtype=np.uint8).tobytes())
+    data = b"".join(parts) + b"ab" * 7
+    want = harness.oracle_encode(data, bs)
+    # block sizes from per-block encodes (every block is coded on its own)
+    residues, off = set(), 0
+    for i in range(0, len(data), bs):
+        residues.add(off % 16)
+        off += len(harness.oracle_encode(data[i:i + bs], bs))
+    assert off == len(want) and len(residues) == 16
+    rc, got = emu.encode(data, bs)
+    assert rc == 0 and got == want
