@@ -44,10 +44,16 @@ def run(x, bs, env, no_overlap, reps=10):
 
 
 x = datagen.zipf_torch(n, dev, 255, seed=2)
-for bs in (65536, 262144, 65536, 262144, 1 << 20, 16384):
+combos = ((8, 4), (8, 4), (8, 4))
+if os.environ.get("AB_SLOTS"):  # e.g. AB_SLOTS=2,4,6,8: one pipeline run per slot count
+    combos = tuple((int(v), 4) for v in os.environ["AB_SLOTS"].split(","))
+sizes = (65536, 262144, 65536, 262144, 1 << 20, 16384)
+if os.environ.get("AB_BS"):
+    sizes = tuple(int(v) for v in os.environ["AB_BS"].split(","))
+for bs in sizes:
     base = run(x, bs, {}, True)
     print(f"bs {bs:8d}  one stream      {base[0]:.3f} ms  {n / base[0] / 1e6:7.1f} GB/s", flush=True)
-    for slots, pass_mib in ((8, 4), (8, 4), (8, 4)):
+    for slots, pass_mib in combos:
         env = {"HUF_B200_ENC_SLOTS": str(slots), "HUF_B200_ENC_PIPE_PASS": str(pass_mib << 20)}
         r = run(x, bs, env, False)
         ok = r[1:] == base[1:]
