@@ -550,3 +550,41 @@ def test_emu_block_headers_at_every_alignment(emu, harness):
     assert off == len(want) and len(residues) == 16
     rc, got = emu.encode(data, bs)
     assert rc == 0 and got == want
+
+
+def _random_case(rng):
+    """A random input: alphabet size, skew (uniform ... a few dominant symbols ... Fibonacci-like
+    counts), length and block size all drawn, so that tie-breaks in the merge, deep and flat
+    trees, ragged last blocks and one-symbol blocks all turn up."""
+    n = int(rng.integers(1, 40000))
+    nsym = int(rng.integers(1, 257))
+    kind = int(rng.integers(0, 4))
+    if kind == 0:
+        data = rng.integers(0, nsym, size=n, dtype=np.uint8)
+    elif kind == 1:
+        p = 1.0 / np.arange(1, nsym + 1) ** float(rng.uniform(0.5, 2.5))
+        data = rng.choice(nsym, size=n, p=p / p.sum()).astype(np.uint8)
+    elif kind == 2:
+        data = np.minimum(rng.geometric(float(rng.uniform(0.2, 0.7)), size=n) - 1, nsym - 1).astype(np.uint8)
+    else:  # runs of equal counts: many ties for the merge order
+        reps = int(rng.integers(1, 6))
+        data = np.repeat(rng.permutation(nsym).astype(np.uint8), reps)
+        data = np.resize(data, n)
+        rng.shuffle(data)
+    perm = rng.permutation(256).astype(np.uint8)  # symbols are not ranks
+    bs = int(rng.choice([0, 300, 1000, 4096, 16384, 65536]))
+    out = perm[data].tobytes()
+    return (out[:20 * bs] if bs else out), bs  # (at most 20 blocks: the emulator runs a CTA at a time)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_emu_random_inputs_bit_exact(emu, harness, seed):
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(8):
+        data, bs = _random_case(rng)
+        want = harness.oracle_encode(data, bs)
+        rc, got = emu.encode(data, bs)
+        assert rc == 0 and got == want, (seed, len(data), bs)
+        # device entry points with the lenient 1025-element mode, so 256-symbol blocks decode too
+        rc, back, _ = _lanes(emu, want, len(data), accept_1025=True)
+        assert rc == 0 and back == data, (seed, len(data), bs)
