@@ -77,7 +77,13 @@ __device__ __forceinline__ void pack_put(PackAcc &s, uint32_t t, uint32_t sum)
     s.pos = n;
 }
 
-__global__ void __launch_bounds__(kEncWarps * 32) k_pack(EncArgs a)
+// (HUF_PACK_MINCTA: build knob of the occupancy experiment -- CTAs per SM the register allocation must allow)
+#ifdef HUF_PACK_MINCTA
+__global__ void __launch_bounds__(kEncWarps * 32, HUF_PACK_MINCTA)
+#else
+__global__ void __launch_bounds__(kEncWarps * 32)
+#endif
+k_pack(EncArgs a)
 {
     __shared__ PackFastSmem sm;
     const int lane = lane_id();
