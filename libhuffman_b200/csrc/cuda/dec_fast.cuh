@@ -2,7 +2,9 @@
 //
 //   K4d k_tree     one LANE per candidate block (32 headers staged in shared memory per warp
 //                  with coalesced loads): serial pre-order walk of the serialised tree (grammar
-//                  of reference src/tree.c:138-208) with a small stack, producing the ordered
+//                  of reference src/tree.c:138-208) -- the slot being filled is known by its left
+//                  aligned path bits and depth, a terminal moves on by adding 2^(32 - depth) and
+//                  the carry of that addition is the pop -- producing the ordered
 //                  list of lookup-table terminals (leaf / absent child / long-code prefix) and
 //                  the shortest code length; leaves below the table reach (13 bits) become
 //                  sorted (code, length, symbol) records that the decoder searches.  Only the

@@ -13,13 +13,9 @@
 //                       through the three kernels of enc_build.cuh (sort / lane-per-block merge
 //                       / codes).
 //       k_scan_sizes    exclusive scan of block byte sizes -> block offsets in the stream.
-//   K3w k_pack_wide     one warp per segment: code lookup, warp scan of code lengths,
-//                       funnel-shift bit packing into a shared staging window, coalesced
-//                       32-bit big-endian word stores; also emits the block header.
-//                       Replaces the header writes (src/encoder.c:325-342) and
-//                       __huf_encode_block + huf_bit_write (src/encoder.c:85-131,
-//                       src/bufio.c:18-32).  Takes the blocks with a code word above 16 bits;
-//                       all others go through k_pack in enc_pack.cuh.
+//   K3  (enc_pack.cuh)  k_pack and k_pack_wide; this file keeps what they share: the owned byte
+//                       range of a segment, the per-symbol accumulator of the ragged ends, the
+//                       segmented carry scan, and the block header (emit_block_header).
 //
 // Data layout in HBM (all sizes for nblocks blocks, nspb segments per block):
 //   seg_hist   u16 [nblocks*nspb][256]    written by K1, read by K2

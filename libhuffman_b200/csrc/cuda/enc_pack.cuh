@@ -1,18 +1,24 @@
-// enc_pack.cuh — K3 fast lane: bit packing for blocks whose longest code word is <= 16 bits
-// (every block of ordinary data; deeper trees and one-symbol blocks take k_pack_wide in
-// enc_kernels.cuh).
+// enc_pack.cuh — K3, the bit packing.
 //
+// k_pack (fast lane): blocks whose longest code word is <= 16 bits (every block of ordinary data).
 // One warp per segment, 16 symbols per lane and iteration.  Code words are looked up with one
 // 4-byte shared-memory load (left-aligned code in the top half, length below: one bank word per
 // entry), two neighbours are concatenated in registers (<= 32 bits), the lane's bit offset comes
-// from a warp scan of the lengths.  Every lane then pushes its eight pairs through a 64-bit
-// accumulator and stores each word it COMPLETES with a plain shared-memory store: sixteen code
-// words of at least two bits fill at least one word, so every word of the window is completed
-// by exactly one lane, and what a lane leaves unfinished behind its last word boundary travels
-// to its right neighbour through one shuffle and is OR-ed into that lane's first word (lane 31's
-// remainder is the carry into the next iteration).  No atomics, no zeroing of the window.
-// Whole 16-byte lines leave as coalesced big-endian stores; only the first and last bytes of a
-// segment, which share a word with a neighbouring segment, are written byte-wise.
+// from a warp scan of the lengths.  Every lane then pushes its eight pairs through a one-word
+// accumulator keyed by its running bit position and stores each word it COMPLETES with a plain
+// shared-memory store: sixteen code words of at least two bits fill at least one word, so every
+// word of the window is completed by exactly one lane, and what a lane leaves unfinished behind
+// its last word boundary travels to its right neighbour through one shuffle and is OR-ed into
+// that lane's first word (lane 31's remainder is the carry into the next iteration).  No atomics,
+// no zeroing of the window.  Whole 16-byte lines leave as coalesced big-endian stores through a
+// running pointer; only the first and last bytes of a segment, which share a word with a
+// neighbouring segment, are written byte-wise.
+//
+// k_pack_wide (general lane, at the end of this file): blocks with a code word of 17 ... 56 bits
+// and one-symbol blocks.  Whole rows of 512 symbols are packed the same way with one put per code
+// word (<= 26 bits, 32-bit table entries) or two (<= 56 bits, 64-bit entries); ragged ends,
+// unaligned buffers and one-symbol blocks take its per-symbol loop with a segmented carry scan.
+//
 // Replaces __huf_encode_block + huf_bit_write (reference src/encoder.c:85-131,
 // src/bufio.c:18-32) and the header writes (src/encoder.c:325-342).
 #pragma once
