@@ -167,8 +167,13 @@ __device__ __forceinline__ uint32_t find_exact(const DecArgs &a, uint64_t o0, ui
     return mask;
 }
 
+// (HUF_FIND_MINCTA: build knob of the occupancy experiment -- CTAs per SM the register allocation must allow)
 template <int MODE>
+#ifdef HUF_FIND_MINCTA
+__global__ void __launch_bounds__(kFindWarps * 32, HUF_FIND_MINCTA) k_find(DecArgs a)
+#else
 __global__ void __launch_bounds__(kFindWarps * 32) k_find(DecArgs a)
+#endif
 {
     constexpr bool EMIT = MODE != 0;
     const int lane = lane_id();
